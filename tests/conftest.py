@@ -1,0 +1,30 @@
+import glob
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[: -len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
+
+
+def load_golden(name):
+    from tensororder_b200.plan_format import PortablePlan
+
+    return PortablePlan.load(os.path.join(GOLDEN_DIR, name + ".json.gz"))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
