@@ -1,0 +1,308 @@
+"""`B200API` — the `--tensor_library=b200` backend.
+
+Mirrors the reference's tensor-library interface for the execution path
+(`BaseTensorAPI`, src/tensor_network/tensor_apis/base_api.py:8-28, and the de-facto members of
+`NumpyAPI`, src/tensor_network/tensor_apis/numpy_apis.py:24-65): same method names, argument
+meaning and error behaviour, so `execution.run` (src/execution.py:122-152) drives it unchanged.
+All arithmetic happens in the CUDA library behind include/tob200.h; there is no CPU fallback.
+
+Multi-GPU: when `torch.distributed` is initialised, rank r contracts slices
+r, r+W, r+2W, ... and the partial counts are combined with one all-reduce (NCCL on GPUs)."""
+from __future__ import annotations
+
+import ctypes
+import time
+from ctypes import byref, c_double, c_float, c_int32, c_void_p
+from typing import Optional
+
+import numpy as np
+
+from . import cabi
+from .flatten import FlatPlan, flatten_plan
+
+
+class OutOfMemoryError(Exception):
+    """Stands in for `tensor_network.OutOfMemoryError` (base_api.py:4) when the reference is not
+    importable; `B200API` raises the reference's own class when it is."""
+
+
+def _oom_class():
+    try:  # the reference package, when this backend is registered inside TensorOrder
+        from tensor_network.tensor_apis.base_api import OutOfMemoryError as RefOOM  # type: ignore
+
+        return RefOOM
+    except Exception:
+        return OutOfMemoryError
+
+
+def _ptr(arr: np.ndarray, ctype):
+    return arr.ctypes.data_as(ctypes.POINTER(ctype))
+
+
+class CompiledPlan:
+    """Owns one `tob_plan` (device arena, leaf tensors, CUDA graph)."""
+
+    def __init__(self, flat: FlatPlan, device: int = 0, use_graph: bool = True, kernel_policy: int = 0,
+                 hoist_invariant: bool = True, mem_limit_bytes: int = 0):
+        self.flat = flat
+        self._handle = c_void_p()
+        desc = cabi.tob_plan_desc()
+        desc.n_nodes = flat.n_nodes
+        desc.node_left = _ptr(flat.node_left, c_int32)
+        desc.node_right = _ptr(flat.node_right, c_int32)
+        desc.node_leaf = _ptr(flat.node_leaf, c_int32)
+        desc.n_leaves = flat.n_leaves
+        desc.leaf_rank = _ptr(flat.leaf_rank, c_int32)
+        desc.leaf_data_offset = _ptr(flat.leaf_data_offset, ctypes.c_int64)
+        desc.leaf_axis_start = _ptr(flat.leaf_axis_start, c_int32)
+        desc.leaf_axis_edge = _ptr(flat.leaf_axis_edge, c_int32)
+        desc.n_slice_groups = flat.n_slice_groups
+        desc.leaf_data_len = int(flat.leaf_data.shape[0])
+        opt = cabi.tob_options()
+        cabi.lib.tob_default_options(byref(opt))
+        opt.device = device
+        opt.use_graph = 1 if use_graph else 0
+        opt.kernel_policy = kernel_policy
+        opt.hoist_invariant = 1 if hoist_invariant else 0
+        opt.mem_limit_bytes = int(mem_limit_bytes)
+        rc = cabi.lib.tob_plan_create(byref(desc), byref(opt), byref(self._handle))
+        if rc != cabi.TOB_OK:
+            raise ValueError("tob_plan_create: " + cabi.last_error())
+        self.uploaded = False
+
+    # -- host-only queries --
+    @property
+    def num_slices(self) -> int:
+        return int(cabi.lib.tob_plan_num_slices(self._handle))
+
+    @property
+    def peak_bytes(self) -> int:
+        return int(cabi.lib.tob_plan_peak_bytes(self._handle))
+
+    @property
+    def num_ops(self) -> int:
+        return int(cabi.lib.tob_plan_num_ops(self._handle))
+
+    def describe(self) -> dict:
+        import json
+
+        n = cabi.lib.tob_plan_describe(self._handle, None, 0)
+        buf = ctypes.create_string_buffer(n + 1)
+        cabi.lib.tob_plan_describe(self._handle, buf, n + 1)
+        return json.loads(buf.value.decode())
+
+    # -- device --
+    def upload(self) -> None:
+        rc = cabi.lib.tob_plan_upload(self._handle, _ptr(self.flat.leaf_data, c_double), int(self.flat.leaf_data.shape[0]))
+        if rc == cabi.TOB_E_OOM:
+            raise _oom_class()(cabi.last_error())
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_upload: " + cabi.last_error())
+        self.uploaded = True
+
+    def run(self, first: int = 0, count: Optional[int] = None, stride: int = 1) -> float:
+        if count is None:
+            count = (self.num_slices - first + stride - 1) // stride
+        out = c_double(0.0)
+        rc = cabi.lib.tob_plan_run(self._handle, first, count, stride, byref(out))
+        if rc == cabi.TOB_E_OOM:
+            raise _oom_class()(cabi.last_error())
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_run: " + cabi.last_error())
+        return out.value
+
+    @property
+    def last_ms(self) -> float:
+        return float(cabi.lib.tob_plan_last_ms(self._handle))
+
+    @property
+    def last_launches(self) -> int:
+        return int(cabi.lib.tob_plan_last_launches(self._handle))
+
+    def profile(self, slice_id: int = 0):
+        n = self.num_ops
+        ms = (c_float * n)()
+        out = c_double(0.0)
+        rc = cabi.lib.tob_plan_profile(self._handle, slice_id, ms, n, byref(out))
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_profile: " + cabi.last_error())
+        return list(ms), out.value
+
+    def close(self) -> None:
+        if self._handle:
+            cabi.lib.tob_plan_destroy(self._handle)
+            self._handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class B200API:
+    """Drop-in for `tensor_network.ALL_APIS[...]` entries (src/tensor_network/__init__.py:12-16)."""
+
+    def __init__(self):
+        self._entry_type = "float64"
+        self._device = None  # None: LOCAL_RANK under torchrun, else 0
+        self._use_graph = True
+        self._kernel_policy = 0
+        self._hoist = True
+        self._distributed = True
+        self.last_stats = {}
+
+    # ---- configuration (tensororder.py:205-217, execution.py:82-85) ----
+    def add_argument(self, key, value):
+        if key == "entry_type":
+            if value != "float64":
+                raise ValueError("Unknown b200 type %s (only float64 is implemented)" % value)
+            self._entry_type = value
+        elif key == "thread_limit":
+            pass  # BLAS thread cap of the numpy backend; no host threads are used here
+        elif key == "device":
+            self._device = int(value)
+        elif key == "use_graph":
+            self._use_graph = bool(value)
+        elif key == "kernel_policy":
+            self._kernel_policy = int(value)
+        elif key == "hoist_invariant":
+            self._hoist = bool(value)
+        elif key == "distributed":
+            self._distributed = bool(value)
+        else:
+            # same message and exception type as BaseTensorAPI.add_argument (base_api.py:9-12)
+            raise ValueError("Invalid argument " + str(key) + " for selected tensor_library")
+
+    def get_entry_size(self):
+        return 8  # numpy.dtype(float64).itemsize, numpy_apis.py:64-65
+
+    def warm(self):
+        self._resolve_device()
+        if cabi.lib.tob_device_count() <= 0:
+            raise RuntimeError("b200 tensor library: no CUDA device")
+
+    # ---- leaf construction: host arrays, like every reference backend (numpy_apis.py:36-40) ----
+    def create_tensor(self, shape, default_value=None):
+        if default_value is None:
+            return np.empty(shape, dtype=np.float64)
+        return np.full(shape, default_value, dtype=np.float64)
+
+    # ---- the primary entry (base_api.py:17-28, called from execution.py:136) ----
+    def contract_sliced(self, execution_plan, num_slice_limit=None):
+        t0 = time.perf_counter()
+        flat = flatten_plan(execution_plan, self.create_tensor)
+        rank, world = self._rank_world()
+        compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
+                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist)
+        try:
+            t1 = time.perf_counter()
+            compiled.upload()
+            t2 = time.perf_counter()
+            total = compiled.num_slices
+            if num_slice_limit is not None:
+                total = min(total, int(num_slice_limit))  # itertools.islice(slices, N), base_api.py:23-24
+            count = 0 if rank >= total else (total - rank + world - 1) // world
+            partial = compiled.run(first=rank if count else 0, count=count, stride=world)
+            t3 = time.perf_counter()
+            result = self._all_reduce(partial) if world > 1 else partial
+            self.last_stats = {
+                "flatten_compile_s": t1 - t0, "upload_s": t2 - t1, "run_s": t3 - t2,
+                "device_ms": compiled.last_ms, "launches": compiled.last_launches,
+                "h2d_bytes": int(flat.leaf_data.nbytes), "d2h_bytes": 32,
+                "peak_bytes": compiled.peak_bytes, "slices": total, "rank": rank, "world": world,
+            }
+        finally:
+            compiled.close()
+        return np.float64(result)
+
+    # ---- secondary entries ----
+    def contract(self, network, contraction_tree):
+        """One (unsliced) network; returns a 0-d array so `result[tuple()]` works (base_api.py:26-27)."""
+
+        class _Plan:
+            pass
+
+        plan = _Plan()
+        plan.tree, plan.network, plan.groups_to_slice = contraction_tree, network, []
+        keep = self._distributed
+        self._distributed = False
+        try:
+            return np.array(self.contract_sliced(plan), dtype=np.float64)
+        finally:
+            self._distributed = keep
+
+    def tensordot(self, a, b, axes):
+        """`numpy.tensordot(a, b, (axes_a, axes_b))` on the GPU for host arrays whose axes all have
+        extent 2 (call site tensor_network.pyx:152-154)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        axes_a, axes_b = axes
+        axes_a = [int(x) % max(a.ndim, 1) for x in np.atleast_1d(axes_a)] if np.size(axes_a) else []
+        axes_b = [int(x) % max(b.ndim, 1) for x in np.atleast_1d(axes_b)] if np.size(axes_b) else []
+        if len(axes_a) != len(axes_b):
+            raise ValueError("shape-mismatch for sum")
+        if any(s != 2 for s in a.shape) or any(s != 2 for s in b.shape):
+            raise ValueError("b200 tensordot: every index must have extent 2")
+        rank_c = a.ndim + b.ndim - 2 * len(axes_a)
+        c = np.empty((2,) * rank_c, dtype=np.float64)
+        aa = np.asarray(axes_a, dtype=np.int32)
+        ab = np.asarray(axes_b, dtype=np.int32)
+        rc = cabi.lib.tob_tensordot_host(_ptr(a, c_double), a.ndim, _ptr(b, c_double), b.ndim, _ptr(aa, c_int32),
+                                         _ptr(ab, c_int32), len(axes_a), _ptr(c, c_double))
+        if rc == cabi.TOB_E_OOM:
+            raise _oom_class()(cabi.last_error())
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_tensordot_host: " + cabi.last_error())
+        return c
+
+    # ---- helpers ----
+    def _resolve_device(self) -> int:
+        if self._device is not None:
+            return self._device
+        import os
+
+        return int(os.environ.get("LOCAL_RANK", "0")) if self._dist_ready() else 0
+
+    def _dist_ready(self) -> bool:
+        if not self._distributed:
+            return False
+        try:
+            import torch.distributed as dist
+
+            return dist.is_available() and dist.is_initialized()
+        except Exception:
+            return False
+
+    def _rank_world(self):
+        if self._dist_ready():
+            import torch.distributed as dist
+
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _all_reduce(self, partial: float) -> float:
+        """One all-reduce of a float64 scalar (the only exchange step of the sliced path)."""
+        import torch
+        import torch.distributed as dist
+
+        backend = dist.get_backend()
+        dev = torch.device("cuda", self._resolve_device()) if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor([partial], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+B200_APIS = {"b200": B200API}
+
+
+def register(all_apis=None):
+    """Adds "b200" to the reference's live registry `tensor_network.ALL_APIS`
+    (src/tensor_network/__init__.py:12-16) — the dict `util.TaggedChoice` resolves `--tensor_library`
+    against (src/tensororder.py:88-94, src/util/util.py:249-252)."""
+    if all_apis is None:
+        import tensor_network  # type: ignore  (the reference package; needs <TensorOrder>/src on sys.path)
+
+        all_apis = tensor_network.ALL_APIS
+    all_apis.update(B200_APIS)
+    return all_apis

@@ -1,0 +1,92 @@
+// Internal types of the B200 contraction executor (host side).  See DESIGN.md §3-§5.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tob200.h"
+
+namespace tob {
+
+// ------------------------------------------------------------------------------------------------
+// Canonical layouts.  Every tensor is dense; address bit p holds one network edge.
+// A tensor that is an operand of a join with sibling S is stored as
+//        [ K' (edges shared with S, ascending edge id) | F' (its other edges, in the parent's
+//          output order) ]            low bits  ------------------------------------>  high bits
+// so every join is   C[pdep(mi,maskM)|pdep(ni,maskN)] = sum_kk A[mi<<k | kk] * B[ni<<k | kk].
+// ------------------------------------------------------------------------------------------------
+enum OpKind : int32_t {
+    OP_GENERIC = 0,  // thread / warp / CTA per output element, bandwidth-bound
+    OP_GEMM = 1,     // DMMA tile kernel, compute-bound
+    OP_ACCUM = 2,    // acc += root scalar
+};
+
+struct OperandRef {
+    int32_t space = 0;       // 0: leaf region, 1: arena
+    int64_t offset = 0;      // doubles from the start of that region
+    int32_t leaf = -1;       // leaf-table index when space == 0 (slice offset lookup), else -1
+    int32_t node = -1;       // post-order position of the producing node
+};
+
+struct Op {
+    int32_t kind = OP_GENERIC;
+    int32_t node = -1;          // post-order position of the join this op computes
+    OperandRef a, b;            // a = "M side", b = "N side" (may be swapped w.r.t. left/right)
+    int64_t c_offset = 0;       // arena offset (doubles) of the result
+    int32_t m = 0, n = 0, k = 0;
+    uint64_t mask_m = 0;        // C address bits fed by mi (ascending); the rest of the low m+n bits by ni
+    // generic kernel configuration
+    int32_t threads_per_out = 1;  // 1, 32 or 256
+    int32_t ksplit_log2 = 0;      // K split across CTAs (partials in the workspace, reduced deterministically)
+    // gemm kernel configuration
+    int32_t tm_log2 = 7, tn_log2 = 7;
+    int64_t ws_offset = -1;     // workspace offset (doubles) for split-K partials
+    int32_t invariant = 0;      // 1: independent of the slice id (hoisted)
+    double flops = 0, bytes = 0;
+};
+
+struct LeafInfo {
+    int32_t rank = 0;                 // stored rank (live + sliced axes)
+    int32_t live_rank = 0;
+    int64_t src_offset = 0;           // doubles, in the caller's leaf buffer (numpy order)
+    int64_t dev_offset = 0;           // doubles, in the device leaf region (canonical order)
+    std::vector<int32_t> axis_edge;   // numpy axis -> edge id or -(g+1)
+    // permutation applied at upload: device address bit p takes source address bit src_bit[p]
+    std::vector<int32_t> src_bit;     // size rank; first live_rank entries are the canonical live layout
+    // slice offset = sum over terms of ((slice_id >> id_bit) & 1) << addr_bit   (doubles)
+    std::vector<int32_t> slice_id_bit, slice_addr_bit;
+};
+
+struct NodeInfo {
+    int32_t left = -1, right = -1, leaf = -1, parent = -1;
+    std::vector<int32_t> edges;       // sorted edge ids
+    std::vector<int32_t> layout;      // canonical layout: layout[p] = edge id at address bit p
+    int32_t k_with_sibling = 0;       // how many low bits of `layout` are contracted at the parent
+    bool slice_dependent = false;
+    OperandRef where;                 // where the node's tensor lives when it is consumed
+};
+
+struct Program {
+    tob_options opt;
+    int32_t n_slice_groups = 0;
+    std::vector<NodeInfo> nodes;
+    std::vector<LeafInfo> leaves;
+    std::vector<Op> invariant_ops;    // run once per tob_plan_run
+    std::vector<Op> slice_ops;        // run once per slice
+    int64_t leaf_doubles = 0;         // device leaf region
+    int64_t arena_doubles = 0;        // intermediates
+    int64_t ws_doubles = 0;           // split-K workspace
+    int64_t src_leaf_len = 0;
+    double total_flops = 0, total_bytes = 0;
+    OperandRef root;                  // rank-0 result of one slice
+};
+
+int compile(const tob_plan_desc* desc, const tob_options* opt, Program* out, std::string* err);
+std::string describe(const Program& p);
+
+// Shared by compile and the stand-alone tensordot: pick kernel + configuration for a canonical join.
+void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk);
+
+void set_error(const std::string& msg);
+
+}  // namespace tob

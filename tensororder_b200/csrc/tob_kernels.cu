@@ -1,0 +1,508 @@
+// Hand-written sm_100a kernels of the contraction executor.
+//
+// Every join arrives in canonical form (tob_internal.h):
+//     C[pdep(mi, mask_m) | pdep(ni, mask_n)] = sum_{kk < 2^k} A[mi << k | kk] * B[ni << k | kk]
+// i.e. a "TN" GEMM with both operands K-contiguous and an interleaving scatter on the output.
+//
+//  * k_gemm_dmma   — compute-bound joins.  FP64 has no tcgen05 kind on Blackwell, so the tensor-core
+//                    path is DMMA (mma.sync.m8n8k4.f64; SASS DMMA.8x8x4).  CTA tile TM x TN x 16,
+//                    multi-stage cp.async (LDGSTS) pipeline of 128-byte rows, padded K-major shared
+//                    memory (conflict-free fragment loads), split-K across CTAs for short grids.
+//  * k_generic_*   — bandwidth/latency-bound joins: one thread, one warp or one CTA per output element,
+//                    vectorised K-contiguous loads, warp-shuffle reductions, deterministic split-K.
+//  * k_permute     — stand-alone index (address-bit) permutation through shared memory.
+//  * k_begin_slice / k_accum — slice bookkeeping kept on the device so a slice replays as a CUDA graph.
+#include <cstdio>
+
+#include "tob_kernels.cuh"
+
+namespace tob {
+
+// ------------------------------------------------------------------------------------------------
+// bit scatter / gather by runs
+// ------------------------------------------------------------------------------------------------
+BitRuns make_runs(uint64_t mask) {
+    BitRuns r;
+    r.n = 0;
+    for (int i = 0; i < 24; i++) r.dst[i] = r.src[i] = r.len[i] = 0;
+    int src = 0;
+    int p = 0;
+    while (p < 64) {
+        if (!((mask >> p) & 1)) { p++; continue; }
+        int q = p;
+        while (q < 64 && ((mask >> q) & 1)) q++;
+        r.dst[r.n] = (uint8_t)p;
+        r.src[r.n] = (uint8_t)src;
+        r.len[r.n] = (uint8_t)(q - p);
+        r.n++;
+        src += q - p;
+        p = q;
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long pext_runs(unsigned long long x, const BitRuns& r) {
+    unsigned long long o = 0;
+    for (int i = 0; i < r.n; i++) o |= ((x >> r.dst[i]) & ((1ull << r.len[i]) - 1ull)) << r.src[i];
+    return o;
+}
+__device__ __forceinline__ unsigned long long pdep_runs(unsigned long long x, const BitRuns& r) {
+    unsigned long long o = 0;
+    for (int i = 0; i < r.n; i++) o |= ((x >> r.src[i]) & ((1ull << r.len[i]) - 1ull)) << r.dst[i];
+    return o;
+}
+
+__device__ __forceinline__ const double* operand_base(const double* base, const long long* leaf_off, int leaf) {
+    return (leaf >= 0) ? base + leaf_off[leaf] : base;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernels
+// ------------------------------------------------------------------------------------------------
+// one thread per output element; K <= 64
+__global__ void __launch_bounds__(256) k_generic_t1(KParams p) {
+    const double* A = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* B = operand_base(p.b, p.leaf_off, p.b_leaf);
+    const unsigned long long total = 1ull << (p.m + p.n);
+    const int k = p.k;
+    for (unsigned long long c = blockIdx.x * 256ull + threadIdx.x; c < total; c += (unsigned long long)gridDim.x * 256ull) {
+        const unsigned long long mi = pext_runs(c, p.runs_m);
+        const unsigned long long ni = pext_runs(c, p.runs_n);
+        const double* ar = A + (mi << k);
+        const double* br = B + (ni << k);
+        double s;
+        if (k == 0) {
+            s = ar[0] * br[0];
+        } else {
+            const double2* a2 = reinterpret_cast<const double2*>(ar);
+            const double2* b2 = reinterpret_cast<const double2*>(br);
+            const int K2 = 1 << (k - 1);
+            s = 0.0;
+            for (int i = 0; i < K2; i++) {
+                const double2 x = a2[i], y = b2[i];
+                s = fma(x.x, y.x, s);
+                s = fma(x.y, y.y, s);
+            }
+        }
+        p.c[c] = s;
+    }
+}
+
+// one warp per output element; 128 <= K
+__global__ void __launch_bounds__(256) k_generic_t32(KParams p) {
+    const double* A = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* B = operand_base(p.b, p.leaf_off, p.b_leaf);
+    const unsigned long long total = 1ull << (p.m + p.n);
+    const int k = p.k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long K2 = 1ull << (k - 1);
+    for (unsigned long long c = blockIdx.x * 8ull + warp; c < total; c += (unsigned long long)gridDim.x * 8ull) {
+        const unsigned long long mi = pext_runs(c, p.runs_m);
+        const unsigned long long ni = pext_runs(c, p.runs_n);
+        const double2* a2 = reinterpret_cast<const double2*>(A + (mi << k));
+        const double2* b2 = reinterpret_cast<const double2*>(B + (ni << k));
+        double s0 = 0.0, s1 = 0.0;
+        for (unsigned long long i = lane; i < K2; i += 32) {
+            const double2 x = a2[i], y = b2[i];
+            s0 = fma(x.x, y.x, s0);
+            s1 = fma(x.y, y.y, s1);
+        }
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) p.c[c] = s;
+    }
+}
+
+// one CTA per (output element, K chunk); K >= 128
+__global__ void __launch_bounds__(256) k_generic_t256(KParams p) {
+    __shared__ double red[8];
+    const double* A = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* B = operand_base(p.b, p.leaf_off, p.b_leaf);
+    const int k = p.k, ks = p.ksplit_log2;
+    const unsigned long long outs = 1ull << (p.m + p.n);
+    const unsigned long long work = outs << ks;
+    const unsigned long long chunk2 = 1ull << (k - ks - 1);  // double2 elements per chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned long long w = blockIdx.x; w < work; w += gridDim.x) {
+        const unsigned long long c = w & (outs - 1);
+        const unsigned long long split = w >> (p.m + p.n);
+        const unsigned long long mi = pext_runs(c, p.runs_m);
+        const unsigned long long ni = pext_runs(c, p.runs_n);
+        const double2* a2 = reinterpret_cast<const double2*>(A + (mi << k)) + split * chunk2;
+        const double2* b2 = reinterpret_cast<const double2*>(B + (ni << k)) + split * chunk2;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        unsigned long long i = threadIdx.x;
+        for (; i + 768 < chunk2; i += 1024) {
+            const double2 x0 = a2[i], y0 = b2[i];
+            const double2 x1 = a2[i + 256], y1 = b2[i + 256];
+            const double2 x2 = a2[i + 512], y2 = b2[i + 512];
+            const double2 x3 = a2[i + 768], y3 = b2[i + 768];
+            s0 = fma(x0.x, y0.x, s0); s0 = fma(x0.y, y0.y, s0);
+            s1 = fma(x1.x, y1.x, s1); s1 = fma(x1.y, y1.y, s1);
+            s2 = fma(x2.x, y2.x, s2); s2 = fma(x2.y, y2.y, s2);
+            s3 = fma(x3.x, y3.x, s3); s3 = fma(x3.y, y3.y, s3);
+        }
+        for (; i < chunk2; i += 256) {
+            const double2 x = a2[i], y = b2[i];
+            s0 = fma(x.x, y.x, s0);
+            s0 = fma(x.y, y.y, s0);
+        }
+        double s = warp_sum((s0 + s1) + (s2 + s3));
+        __syncthreads();  // red[] reuse across iterations of the work loop
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            s = (lane < 8) ? red[lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (ks > 0) p.ws[split * outs + c] = s;
+                else p.c[c] = s;
+            }
+        }
+    }
+}
+
+// C[o] = sum_j ws[j * outs + o], j ascending (deterministic)
+__global__ void __launch_bounds__(256) k_reduce_splits(const double* __restrict__ ws, double* __restrict__ c,
+                                                      unsigned long long outs, int nsplit) {
+    for (unsigned long long o = blockIdx.x * 256ull + threadIdx.x; o < outs; o += (unsigned long long)gridDim.x * 256ull) {
+        double s = ws[o];
+        for (int j = 1; j < nsplit; j++) s += ws[(unsigned long long)j * outs + o];
+        c[o] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int GEMM_TK = 16;   // doubles per K step: one 128-byte line per tile row
+constexpr int GEMM_LDS = 20;  // shared-memory row stride in doubles (== 4 mod 16: conflict-free fragments)
+
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int WTM = TM / WM, WTN = TN / WN;  // warp tile
+    constexpr int MB = WTM / 8, NB = WTN / 8;    // 8x8 DMMA blocks per warp tile
+    static_assert(WM * WN == 8, "8 warps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * GEMM_LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * GEMM_LDS);
+    unsigned long long* cN = cM + TM;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    const int k = p.k, ks = p.ksplit_log2;
+
+    for (int i = tid; i < TM; i += 256) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += 256) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+
+    // ---- work decode: 1-D grid over (split, tile), tiles rasterised in groups of 16 M-tiles ----
+    const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
+    const unsigned long long tiles = tilesM * tilesN;
+    const unsigned long long id = blockIdx.x;
+    const unsigned long long split = id / tiles, tid_in = id % tiles;
+    const unsigned long long group = tilesM < 16 ? tilesM : 16;
+    const unsigned long long per_group = group * tilesN;
+    const unsigned long long gidx = tid_in / per_group, r = tid_in % per_group;
+    const unsigned long long tile_m = gidx * group + (r % group), tile_n = r / group;
+
+    const unsigned long long Ksplit = (1ull << k) >> ks;
+    const int KT = (int)(Ksplit / GEMM_TK);
+    const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
+    const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
+
+    const int chunk = tid & 7, row0 = tid >> 3;
+    auto load_stage = [&](int s, int kt) {
+        double* as = As + s * TM * GEMM_LDS;
+        double* bs = Bs + s * TN * GEMM_LDS;
+#pragma unroll
+        for (int i = 0; i < TM / 32; i++) {
+            const int row = row0 + 32 * i;
+            cp_async16(as + row * GEMM_LDS + chunk * 2, A + ((unsigned long long)row << k) + kt * GEMM_TK + chunk * 2);
+        }
+#pragma unroll
+        for (int i = 0; i < TN / 32; i++) {
+            const int row = row0 + 32 * i;
+            cp_async16(bs + row * GEMM_LDS + chunk * 2, B + ((unsigned long long)row << k) + kt * GEMM_TK + chunk * 2);
+        }
+    };
+
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nk = kt + STAGES - 1;
+        if (nk < KT) load_stage(nk % STAGES, nk);
+        cp_async_commit();
+        const double* as = As + (kt % STAGES) * TM * GEMM_LDS + (wm * WTM + g) * GEMM_LDS + t;
+        const double* bs = Bs + (kt % STAGES) * TN * GEMM_LDS + (wn * WTN + g) * GEMM_LDS + t;
+#pragma unroll
+        for (int k4 = 0; k4 < GEMM_TK / 4; k4++) {
+            double af[MB], bf[NB];
+#pragma unroll
+            for (int i = 0; i < MB; i++) af[i] = as[i * 8 * GEMM_LDS + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < NB; j++) bf[j] = bs[j * 8 * GEMM_LDS + k4 * 4];
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: scatter the tile into C (or the split-K workspace) ----
+    double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
+    const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+    const bool vec = (p.mask_n & 1ull) != 0;  // ni bit 0 is C address bit 0: the two fragment columns are adjacent
+#pragma unroll
+    for (int i = 0; i < MB; i++) {
+        const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const int col = wn * WTN + j * 8 + 2 * t;
+            if (vec) {
+                *reinterpret_cast<double2*>(Cout + (rbase | cN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                Cout[rbase | cN[col]] = acc[i][j][0];
+                Cout[rbase | cN[col + 1]] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+template <int TM_LOG2, int TN_LOG2, int STAGES>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * GEMM_LDS * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
+}
+
+#define GEMM_77 k_gemm_dmma<7, 7, 2, 4, 4>
+#define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 4>
+#define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 4>
+
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(GEMM_77, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 4>());
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slice bookkeeping
+// ------------------------------------------------------------------------------------------------
+__global__ void k_begin_slice(DevState* st, SliceTables t) {
+    __shared__ unsigned long long sid;
+    if (threadIdx.x == 0) sid = st->next_slice;
+    __syncthreads();
+    for (int l = threadIdx.x; l < t.n_leaves; l += blockDim.x) {
+        long long off = 0;
+        for (int j = t.term_start[l]; j < t.term_start[l + 1]; j++)
+            off |= (long long)((sid >> t.id_bit[j]) & 1ull) << t.addr_bit[j];
+        t.leaf_off[l] = off;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st->next_slice = sid + st->stride;
+}
+
+__global__ void k_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf) {
+    const double* r = operand_base(root, leaf_off, root_leaf);
+    st->acc += r[0];
+}
+
+cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream) {
+    k_begin_slice<<<1, 256, 0, stream>>>(st, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, cudaStream_t stream) {
+    k_accum<<<1, 1, 0, stream>>>(st, root, leaf_off, root_leaf);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// contract launcher
+// ------------------------------------------------------------------------------------------------
+static unsigned grid_for(unsigned long long items, unsigned long long per_block, unsigned long long cap) {
+    unsigned long long b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (unsigned)b;
+}
+
+cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches) {
+    const unsigned long long outs = 1ull << (op.m + op.n);
+    const unsigned long long cap = 1ull << 30;
+    if (op.kind == OP_GEMM) {
+        const unsigned long long tiles = 1ull << ((op.m - op.tm_log2) + (op.n - op.tn_log2));
+        const unsigned long long blocks = tiles << op.ksplit_log2;
+        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+        if (op.tm_log2 == 7 && op.tn_log2 == 7)
+            GEMM_77<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 4>(), stream>>>(p);
+        else if (op.tm_log2 == 7 && op.tn_log2 == 6)
+            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 4>(), stream>>>(p);
+        else if (op.tm_log2 == 6 && op.tn_log2 == 6)
+            GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 4>(), stream>>>(p);
+        else
+            return cudaErrorInvalidConfiguration;
+        (*launches)++;
+    } else if (op.threads_per_out == 1) {
+        k_generic_t1<<<grid_for(outs, 256, cap), 256, 0, stream>>>(p);
+        (*launches)++;
+    } else if (op.threads_per_out == 32) {
+        k_generic_t32<<<grid_for(outs, 8, cap), 256, 0, stream>>>(p);
+        (*launches)++;
+    } else {
+        k_generic_t256<<<grid_for(outs << op.ksplit_log2, 1, cap), 256, 0, stream>>>(p);
+        (*launches)++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (op.ksplit_log2 > 0) {
+        k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2);
+        (*launches)++;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index permutation:  out[o] = in[sigma(o)],  address bit p of o comes from address bit src_bit[p]
+// ------------------------------------------------------------------------------------------------
+template <int EPT>  // tile elements per thread (tile = 256 * EPT elements)
+__global__ void __launch_bounds__(256) k_permute(PermuteParams p) {
+    extern __shared__ double tile[];
+    const int tid = threadIdx.x;
+    unsigned long long in_off[EPT], out_off[EPT];
+    unsigned tile_idx[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+        const unsigned ei = tid + 256 * e;  // tile index, input order
+        unsigned long long io = 0, oo = 0;
+        unsigned ti = 0;
+        for (int j = 0; j < p.tbits; j++) {
+            const unsigned long long bi = (ei >> j) & 1u;
+            io |= bi << p.in_pos[j];
+            ti |= (unsigned)bi << p.in_to_tile[j];
+            oo |= bi << p.out_pos[j];  // the same index read in output order
+        }
+        in_off[e] = io;
+        tile_idx[e] = ti;
+        out_off[e] = oo;
+    }
+    const unsigned long long ntiles = 1ull << p.nrest;
+    for (unsigned long long tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+        unsigned long long base_in = 0, base_out = 0;
+        for (int j = 0; j < p.nrest; j++) {
+            const unsigned long long b = (tb >> j) & 1ull;
+            base_in |= b << p.rest_in[j];
+            base_out |= b << p.rest_out[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; e++) tile[tile_idx[e]] = p.in[base_in | in_off[e]];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; e++) p.out[base_out | out_off[e]] = tile[tid + 256 * e];
+    }
+}
+
+// tensors smaller than one tile
+__global__ void k_permute_small(const double* in, double* out, int rank, PermuteParams p) {
+    const unsigned long long total = 1ull << rank;
+    for (unsigned long long o = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; o < total;
+         o += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long i = 0;
+        for (int j = 0; j < rank; j++) i |= ((o >> p.rest_out[j]) & 1ull) << p.rest_in[j];
+        out[o] = in[i];
+    }
+}
+
+cudaError_t launch_permute(const double* in, double* out, int rank, const int32_t* src_bit, cudaStream_t stream) {
+    PermuteParams p;
+    p.in = in;
+    p.out = out;
+    p.rank = rank;
+    if (rank < 8) {
+        p.tbits = 0;
+        p.nrest = rank;
+        for (int j = 0; j < rank; j++) { p.rest_out[j] = (uint8_t)j; p.rest_in[j] = (uint8_t)src_bit[j]; }
+        k_permute_small<<<1, 256, 0, stream>>>(in, out, rank, p);
+        return cudaGetLastError();
+    }
+    // tile = low TB output bits  U  output bits fed by the low TB input bits, padded to >= 8 bits
+    const int TB = rank >= 12 ? 6 : 4;
+    bool in_tile[64] = {false};
+    int tbits = 0;
+    for (int q = 0; q < rank; q++)
+        if (q < TB || src_bit[q] < TB) { in_tile[q] = true; tbits++; }
+    for (int q = 0; q < rank && tbits < 8; q++)
+        if (!in_tile[q]) { in_tile[q] = true; tbits++; }
+    // output order of the tile bits
+    int outs[16], n = 0;
+    for (int q = 0; q < rank; q++)
+        if (in_tile[q]) outs[n++] = q;
+    // input order: sort tile bits by their source position
+    int order[16];
+    for (int j = 0; j < n; j++) order[j] = j;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++)
+            if (src_bit[outs[order[b]]] < src_bit[outs[order[a]]]) { int tmp = order[a]; order[a] = order[b]; order[b] = tmp; }
+    p.tbits = n;
+    for (int j = 0; j < n; j++) {
+        p.out_pos[j] = (uint8_t)outs[j];
+        p.in_pos[j] = (uint8_t)src_bit[outs[order[j]]];
+        p.in_to_tile[j] = (uint8_t)order[j];
+    }
+    // out_off[] in the kernel is computed from the same thread index interpreted in OUTPUT order
+    p.nrest = 0;
+    for (int q = 0; q < rank; q++)
+        if (!in_tile[q]) { p.rest_out[p.nrest] = (uint8_t)q; p.rest_in[p.nrest] = (uint8_t)src_bit[q]; p.nrest++; }
+    const unsigned long long ntiles = 1ull << p.nrest;
+    const unsigned blocks = (unsigned)(ntiles < 148ull * 8 ? ntiles : 148ull * 8);
+    const size_t smem = ((size_t)1 << n) * 8;
+    switch (n - 8) {
+        case 0: k_permute<1><<<blocks, 256, smem, stream>>>(p); break;
+        case 1: k_permute<2><<<blocks, 256, smem, stream>>>(p); break;
+        case 2: k_permute<4><<<blocks, 256, smem, stream>>>(p); break;
+        case 3: k_permute<8><<<blocks, 256, smem, stream>>>(p); break;
+        case 4: k_permute<16><<<blocks, 256, smem, stream>>>(p); break;
+        default: return cudaErrorInvalidConfiguration;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace tob

@@ -1,0 +1,66 @@
+// Device-side parameter blocks and launchers (sm_100a).  See tob_kernels.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tob_internal.h"
+
+namespace tob {
+
+// A mask split into runs of adjacent set bits: pdep/pext in a handful of shift+and ops.
+struct BitRuns {
+    int32_t n;
+    uint8_t dst[24];  // position of the run in the scattered word
+    uint8_t src[24];  // position of the run in the compact word
+    uint8_t len[24];
+};
+BitRuns make_runs(uint64_t mask);
+
+struct KParams {
+    const double* a;
+    const double* b;
+    double* c;
+    double* ws;                 // split-K partials (or nullptr)
+    const long long* leaf_off;  // per-leaf slice offsets in doubles (device), may be nullptr
+    int32_t a_leaf, b_leaf;     // index into leaf_off, or -1
+    int32_t m, n, k;
+    int32_t ksplit_log2;
+    uint64_t mask_m, mask_n;
+    BitRuns runs_m, runs_n;
+};
+
+struct DevState {
+    unsigned long long next_slice;
+    unsigned long long stride;
+    double acc;
+    double pad;
+};
+
+struct SliceTables {            // device pointers
+    const int32_t* term_start;  // [n_leaves+1]
+    const uint8_t* id_bit;      // per term: bit of the slice id
+    const uint8_t* addr_bit;    // per term: address bit it selects
+    long long* leaf_off;        // [n_leaves] out
+    int32_t n_leaves;
+};
+
+struct PermuteParams {
+    const double* in;
+    double* out;
+    int32_t rank;
+    int32_t tbits;              // tile bits
+    uint8_t in_pos[16];         // tile bit j (input order) -> input address bit
+    uint8_t in_to_tile[16];     // tile bit j (input order) -> bit index in the output-ordered tile index
+    uint8_t out_pos[16];        // tile bit j (output order) -> output address bit
+    int32_t nrest;              // non-tile bits
+    uint8_t rest_out[40];       // rest bit j -> output address bit
+    uint8_t rest_in[40];        // rest bit j -> input address bit
+};
+
+cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
+cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, cudaStream_t stream);
+cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream);
+cudaError_t launch_permute(const double* in, double* out, int rank, const int32_t* src_bit, cudaStream_t stream);
+cudaError_t configure_kernels();
+
+}  // namespace tob

@@ -1,0 +1,118 @@
+"""Flattens a sliced execution plan (reference objects or a stored plan) into the C arrays of
+`tob_plan_desc` (include/tob200.h).
+
+Reads, by duck typing, exactly what the reference's own backends read:
+  * `plan.tree.iterate_postorder()`, node `.is_leaf` / `.tensor_index`
+    (src/contraction_methods/contraction_tree.pyx:13-27,174-183);
+  * `plan.network.index_list(t)`, `plan.network[t].build(factory)`, `.shape`
+    (src/tensor_network/tensor_network.pyx:23-39, src/tensor_network/tensor.py:33-34);
+  * `plan.groups_to_slice` (src/tensor_network/sliced_execution_plan.py:17-18).
+Slicing follows the JAX backend's scheme (jax_apis.py:253-277): the sliced axes leave the tree
+(`remove_sliced_indices_from`, tensor_network.pyx:444-468) and each leaf is indexed by the slice
+assignment (`get_tensor_slices`, tensor_network.pyx:404-442); empty groups are skipped exactly as
+`slice_groups` skips them (tensor_network.pyx:371-373)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import numpy as np
+
+
+@dataclass
+class FlatPlan:
+    node_left: np.ndarray
+    node_right: np.ndarray
+    node_leaf: np.ndarray
+    leaf_rank: np.ndarray
+    leaf_data_offset: np.ndarray
+    leaf_axis_start: np.ndarray
+    leaf_axis_edge: np.ndarray
+    leaf_data: np.ndarray  # float64, every leaf C-ordered
+    n_slice_groups: int
+    leaf_tensor_index: List[int]
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.node_left.shape[0])
+
+    @property
+    def n_leaves(self) -> int:
+        return int(self.leaf_rank.shape[0])
+
+
+def _host_factory(shape, default_value=None):
+    if default_value is None:
+        return np.empty(shape, dtype=np.float64)
+    return np.full(shape, default_value, dtype=np.float64)
+
+
+def flatten_plan(plan, tensor_factory=_host_factory) -> FlatPlan:
+    network = plan.network
+    # edge id -> slice group index (non-empty groups only, in order)
+    group_of = {}
+    n_groups = 0
+    for group in plan.groups_to_slice:
+        if len(group) == 0:
+            continue
+        for e in group:
+            group_of[int(e)] = n_groups
+        n_groups += 1
+
+    node_left: List[int] = []
+    node_right: List[int] = []
+    node_leaf: List[int] = []
+    leaf_rank: List[int] = []
+    leaf_off: List[int] = []
+    axis_start: List[int] = [0]
+    axis_edge: List[int] = []
+    leaf_tensor_index: List[int] = []
+    chunks: List[np.ndarray] = []
+    built_at = {}  # tensor index -> offset (a tensor named by two leaves is stored once)
+    total = 0
+    stack: List[int] = []
+    for node in plan.tree.iterate_postorder():
+        pos = len(node_left)
+        if node.is_leaf:
+            t = int(node.tensor_index)
+            edges = [int(e) for e in network.index_list(t)]
+            for e in edges:
+                if e < 0:
+                    raise ValueError("tensor %d has a dangling index; the network cannot contract to a scalar" % t)
+            if t not in built_at:
+                data = np.ascontiguousarray(network[t].build(tensor_factory), dtype=np.float64)
+                if data.size != 2 ** len(edges):
+                    raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
+                built_at[t] = total
+                chunks.append(data.reshape(-1))
+                total += data.size
+            node_left.append(-1)
+            node_right.append(-1)
+            node_leaf.append(len(leaf_rank))
+            leaf_rank.append(len(edges))
+            leaf_off.append(built_at[t])
+            axis_edge.extend(-(group_of[e] + 1) if e in group_of else e for e in edges)
+            axis_start.append(len(axis_edge))
+            leaf_tensor_index.append(t)
+        else:
+            right = stack.pop()
+            left = stack.pop()
+            node_left.append(left)
+            node_right.append(right)
+            node_leaf.append(-1)
+        stack.append(pos)
+    if len(stack) != 1:
+        raise ValueError("contraction tree is not a single rooted tree")
+    leaf_data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.float64)
+    return FlatPlan(
+        node_left=np.asarray(node_left, dtype=np.int32),
+        node_right=np.asarray(node_right, dtype=np.int32),
+        node_leaf=np.asarray(node_leaf, dtype=np.int32),
+        leaf_rank=np.asarray(leaf_rank, dtype=np.int32),
+        leaf_data_offset=np.asarray(leaf_off, dtype=np.int64),
+        leaf_axis_start=np.asarray(axis_start, dtype=np.int32),
+        leaf_axis_edge=np.asarray(axis_edge, dtype=np.int32),
+        leaf_data=np.ascontiguousarray(leaf_data, dtype=np.float64),
+        n_slice_groups=n_groups,
+        leaf_tensor_index=leaf_tensor_index,
+    )

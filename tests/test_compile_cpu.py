@@ -1,0 +1,118 @@
+"""Host-side logic without a GPU: the C-ABI library loads and exports every declared symbol, the plan
+flattener + C++ plan compiler produce programs whose canonical-form semantics reproduce the reference
+counts (interpreted in numpy by tests/program_sim.py), error paths behave like the reference's."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO, golden_names, load_golden
+from program_sim import run_program
+from tensororder_b200 import cabi
+from tensororder_b200.api import B200API, CompiledPlan
+from tensororder_b200.flatten import flatten_plan
+
+ALL = golden_names()
+SMALL = [n for n in ALL if load_golden(n).expected.get("maxrank", 99) <= 19]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "tob200.h")).read()
+    declared = set(re.findall(r"\b(tob_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(cabi.SYMBOLS), (declared ^ set(cabi.SYMBOLS))
+    for name in declared:
+        assert hasattr(cabi.lib, name), name
+    assert b"sm_100a" in cabi.lib.tob_version()
+
+
+def test_add_argument_contract():
+    api = B200API()
+    api.add_argument("entry_type", "float64")
+    assert api.get_entry_size() == 8
+    with pytest.raises(ValueError):
+        api.add_argument("entry_type", "float32")
+    with pytest.raises(ValueError, match="Invalid argument"):
+        api.add_argument("TPU", "1.2.3.4")  # base_api.py:9-12
+    t = api.create_tensor((2, 2), 1)
+    assert t.dtype == np.float64 and t.sum() == 4
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_compiled_program_reproduces_reference_count(name):
+    pp = load_golden(name)
+    flat = flatten_plan(pp.as_execution_plan())
+    cp = CompiledPlan(flat)
+    desc = cp.describe()
+    got = run_program(desc, flat)
+    assert math.isclose(got, pp.expected["count"], rel_tol=1e-12), (got, pp.expected["count"])
+    assert cp.peak_bytes >= 8 * (desc["leaf_doubles"] + desc["arena_doubles"])
+    cp.close()
+
+
+def _small_variants():
+    out = []
+    for name in SMALL:
+        pp = load_golden(name)
+        for i, v in enumerate(pp.variants):
+            if "count" in v.get("expected", {}) and v["expected"]["num_slices"] <= 32:
+                out.append((name, i))
+    return out
+
+
+@pytest.mark.parametrize("name,vi", _small_variants())
+@pytest.mark.parametrize("hoist", [True, False])
+def test_compiled_sliced_program(name, vi, hoist):
+    pp = load_golden(name).variant(vi)
+    flat = flatten_plan(pp.as_execution_plan())
+    cp = CompiledPlan(flat, hoist_invariant=hoist)
+    desc = cp.describe()
+    assert cp.num_slices == pp.expected["num_slices"]
+    got = run_program(desc, flat)
+    assert math.isclose(got, pp.expected["count"], rel_tol=1e-12)
+    if "per_slice" in pp.expected:
+        # the multi-GPU partition: rank r of 2 takes slices r, r+2, ...
+        parts = [run_program(desc, flat, first=r, stride=2) for r in range(2)]
+        assert math.isclose(sum(parts), pp.expected["count"], rel_tol=1e-12)
+        assert math.isclose(parts[1], sum(pp.expected["per_slice"][1::2]), rel_tol=1e-12)
+    if "slice_cutoff" in pp.expected:
+        got_cut = run_program(desc, flat, first=0, count=pp.expected["slice_cutoff"])
+        assert math.isclose(got_cut, pp.expected["count_cutoff"], rel_tol=1e-12)
+    if hoist:
+        assert all(op["invariant"] == 1 for op in desc["invariant_ops"])
+        assert all(op["invariant"] == 0 for op in desc["slice_ops"] if op["kind"] != 2)
+    cp.close()
+
+
+def test_forced_generic_policy_and_gemm_selection():
+    pp = load_golden("vc150_lineflow")
+    flat = flatten_plan(pp.as_execution_plan())
+    auto = CompiledPlan(flat).describe()
+    kinds = [op["kind"] for op in auto["slice_ops"]]
+    assert 1 in kinds, "the dominant joins of n=150 must go to the DMMA GEMM kernel"
+    for op in auto["slice_ops"]:
+        if op["kind"] == 1:
+            assert op["m"] >= op["n"] >= 6 and op["k"] >= 4
+            assert op["k"] - op["ksplit_log2"] >= 7 or op["ksplit_log2"] == 0
+    forced = CompiledPlan(flat, kernel_policy=1).describe()
+    assert all(op["kind"] in (0, 2) for op in forced["slice_ops"])
+
+
+def test_plan_errors():
+    pp = load_golden("toy_path_lineflow")
+    plan = pp.as_execution_plan()
+    flat = flatten_plan(plan)
+    # open index: drop the last join so the root keeps free edges
+    bad = flatten_plan(plan)
+    bad.node_left = bad.node_left[:-1].copy()
+    bad.node_right = bad.node_right[:-1].copy()
+    bad.node_leaf = bad.node_leaf[:-1].copy()
+    with pytest.raises(ValueError):
+        CompiledPlan(bad)
+    cp = CompiledPlan(flat)
+    if cabi.lib.tob_device_count() == 0:
+        with pytest.raises(RuntimeError, match="CUDA device"):
+            cp.upload()  # no CPU fallback: fails loudly without a GPU
+    cp.close()

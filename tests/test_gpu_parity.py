@@ -1,0 +1,130 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden counts and the oracle.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+ALL = golden_names()
+REL = 1e-9  # north_star tolerance for float64 counts that are not exactly representable / weighted
+
+
+def _api(**kw):
+    from tensororder_b200.api import B200API
+
+    api = B200API()
+    api.add_argument("entry_type", "float64")
+    for k, v in kw.items():
+        api.add_argument(k, v)
+    return api
+
+
+def _check(got, exp):
+    want = exp["count"]
+    if want < 2 ** 53 and float(want).is_integer():
+        assert float(got) == want, (got, want)  # unweighted, exactly representable: bit exact
+    else:
+        assert math.isclose(float(got), want, rel_tol=REL), (got, want)
+
+
+def test_readme_instance():
+    pp = load_golden("vc50_lineflow")
+    got = _api().contract_sliced(pp.as_execution_plan())
+    assert str(got) == "2802717837.0"  # what `Count:` prints, tensororder.py:299
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if "count" in load_golden(n).expected])
+@pytest.mark.parametrize("policy", [0, 1])
+def test_unsliced_counts(name, policy):
+    pp = load_golden(name)
+    if policy == 1 and pp.expected["maxrank"] > 24:
+        pytest.skip("generic-only policy is a debug path; too slow for the big GEMM nodes")
+    api = _api(kernel_policy=policy)
+    got = api.contract_sliced(pp.as_execution_plan())
+    _check(got, pp.expected)
+    assert api.last_stats["launches"] > 0
+
+
+def _variants():
+    out = []
+    for name in ALL:
+        pp = load_golden(name)
+        for i, v in enumerate(pp.variants):
+            if "count" in v.get("expected", {}):
+                out.append((name, i))
+    return out
+
+
+@pytest.mark.parametrize("name,vi", _variants())
+@pytest.mark.parametrize("graph", [True, False])
+def test_sliced_counts(name, vi, graph):
+    pp = load_golden(name).variant(vi)
+    api = _api(use_graph=graph)
+    got = api.contract_sliced(pp.as_execution_plan())
+    _check(got, pp.expected)
+    if "slice_cutoff" in pp.expected:
+        cut = api.contract_sliced(pp.as_execution_plan(), num_slice_limit=pp.expected["slice_cutoff"])
+        assert math.isclose(float(cut), pp.expected["count_cutoff"], rel_tol=REL)
+
+
+@pytest.mark.parametrize("name,vi", [x for x in _variants() if "per_slice" in load_golden(x[0]).variants[x[1]]["expected"]][:8])
+def test_per_slice_results_and_partition(name, vi):
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name).variant(vi)
+    cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), hoist_invariant=True)
+    cp.upload()
+    per = pp.expected["per_slice"]
+    for s in range(min(len(per), 16)):
+        assert math.isclose(cp.run(first=s, count=1), per[s], rel_tol=REL, abs_tol=0.0)
+    for world in (2, 4):
+        if len(per) >= world:
+            parts = [cp.run(first=r, stride=world) for r in range(world)]
+            assert math.isclose(sum(parts), pp.expected["count"], rel_tol=REL)
+    cp.close()
+
+
+def test_hoisting_does_not_change_result():
+    pp = load_golden("vc100_lineflow").variant("min4")
+    a = _api(hoist_invariant=True).contract_sliced(pp.as_execution_plan())
+    b = _api(hoist_invariant=False).contract_sliced(pp.as_execution_plan())
+    assert math.isclose(float(a), float(b), rel_tol=1e-12)
+    _check(a, pp.expected)
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if "count" not in load_golden(n).expected])
+def test_large_instances_slicing_invariance(name):
+    """No reference count is stored for the largest family members (numpy needs minutes and tens of
+    GB); size-independent property instead: the count is invariant under the reference slicer's
+    slicings of the same tree."""
+    pp = load_golden(name)
+    if pp.expected["maxrank"] > 29:
+        pytest.skip("covered by bench.py (seconds-long)")
+    base = float(_api().contract_sliced(pp.as_execution_plan()))
+    assert base > 0 and math.isfinite(base)
+    for i, v in enumerate(pp.variants):
+        got = float(_api().contract_sliced(pp.variant(i).as_execution_plan()))
+        assert math.isclose(got, base, rel_tol=REL), (v["name"], got, base)
+
+
+def test_contract_single_network_entry():
+    pp = load_golden("vc50_factorflow")
+    plan = pp.as_execution_plan()
+    res = _api().contract(plan.network, plan.tree)
+    assert res[tuple()] == 2802717837.0  # base_api.py:26-27 indexes the result with ()
+
+
+def test_out_of_memory_maps_to_reference_error():
+    from tensororder_b200.api import CompiledPlan, OutOfMemoryError
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden("vc150_lineflow")
+    cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), mem_limit_bytes=1 << 20)
+    with pytest.raises(OutOfMemoryError):
+        cp.upload()
+    cp.close()
