@@ -64,7 +64,8 @@ typedef struct {
 
 typedef struct {
     int32_t device;          /* CUDA device ordinal                                                        */
-    int32_t use_graph;       /* 1: replay each slice as a CUDA graph (default), 0: plain stream launches   */
+    int32_t use_graph;       /* 2 (default): CUDA graph per slice when the slice is launch-bound, plain     */
+                             /* stream launches (with per-GEMM CUDA events) otherwise; 1 always; 0 never   */
     int32_t kernel_policy;   /* 0 auto, 1 force the generic kernel for every join (debug / parity)         */
     int32_t hoist_invariant; /* 1: compute slice-invariant subtrees once (default), 0: per slice           */
     int64_t mem_limit_bytes; /* 0: use free device memory; else refuse (TOB_E_OOM) plans needing more      */
@@ -102,6 +103,15 @@ double tob_plan_last_ms(const tob_plan* plan);
 
 /* Number of kernels launched by the last tob_plan_run. */
 int64_t tob_plan_last_launches(const tob_plan* plan);
+
+/* DMMA GEMM launches of the last tob_plan_run when it ran as plain stream launches: summed CUDA-event
+ * duration, algorithmic flops (2*2^(fL+fR+k) per join) and launch count.  All zero
+ * when the run was replayed as a graph. */
+int tob_plan_last_gemm(const tob_plan* plan, double* ms, double* flops, int64_t* launches);
+
+/* Run on a caller-owned CUDA stream (cudaStream_t) instead of the plan's own; call after
+ * tob_plan_upload.  The caller keeps the stream alive for the life of the plan. */
+int tob_plan_set_stream(tob_plan* plan, void* stream);
 
 /* Runs one slice op by op with CUDA events around every op; ms_per_op has n_ops entries
  * (tob_plan_num_ops).  Used for the per-node roofline report. */

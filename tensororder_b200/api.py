@@ -42,7 +42,7 @@ def _ptr(arr: np.ndarray, ctype):
 class CompiledPlan:
     """Owns one `tob_plan` (device arena, leaf tensors, CUDA graph)."""
 
-    def __init__(self, flat: FlatPlan, device: int = 0, use_graph: bool = True, kernel_policy: int = 0,
+    def __init__(self, flat: FlatPlan, device: int = 0, use_graph=None, kernel_policy: int = 0,
                  hoist_invariant: bool = True, mem_limit_bytes: int = 0):
         self.flat = flat
         self._handle = c_void_p()
@@ -61,7 +61,8 @@ class CompiledPlan:
         opt = cabi.tob_options()
         cabi.lib.tob_default_options(byref(opt))
         opt.device = device
-        opt.use_graph = 1 if use_graph else 0
+        if use_graph is not None:  # None keeps the library default (auto)
+            opt.use_graph = int(use_graph) if not isinstance(use_graph, bool) else (1 if use_graph else 0)
         opt.kernel_policy = kernel_policy
         opt.hoist_invariant = 1 if hoist_invariant else 0
         opt.mem_limit_bytes = int(mem_limit_bytes)
@@ -119,6 +120,18 @@ class CompiledPlan:
     def last_launches(self) -> int:
         return int(cabi.lib.tob_plan_last_launches(self._handle))
 
+    @property
+    def last_gemm(self):
+        """(ms, flops, launches) of the DMMA GEMM kernels in the last run (stream mode only)."""
+        ms, fl, n = c_double(0), c_double(0), ctypes.c_int64(0)
+        cabi.lib.tob_plan_last_gemm(self._handle, byref(ms), byref(fl), byref(n))
+        return ms.value, fl.value, n.value
+
+    def set_stream(self, cuda_stream_handle: int) -> None:
+        rc = cabi.lib.tob_plan_set_stream(self._handle, c_void_p(cuda_stream_handle))
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_set_stream: " + cabi.last_error())
+
     def profile(self, slice_id: int = 0):
         n = self.num_ops
         ms = (c_float * n)()
@@ -146,7 +159,7 @@ class B200API:
     def __init__(self):
         self._entry_type = "float64"
         self._device = None  # None: LOCAL_RANK under torchrun, else 0
-        self._use_graph = True
+        self._use_graph = None  # library default: graph replay for launch-bound slices
         self._kernel_policy = 0
         self._hoist = True
         self._distributed = True
@@ -163,7 +176,7 @@ class B200API:
         elif key == "device":
             self._device = int(value)
         elif key == "use_graph":
-            self._use_graph = bool(value)
+            self._use_graph = value
         elif key == "kernel_policy":
             self._kernel_policy = int(value)
         elif key == "hoist_invariant":

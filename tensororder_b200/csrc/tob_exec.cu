@@ -44,6 +44,11 @@ struct tob_plan {
     double last_ms = 0;
     int64_t last_launches = 0;
     int64_t graph_launches_per_slice = 0;
+    cudaStream_t own_stream = nullptr;
+    std::vector<cudaEvent_t> gemm_events;  // pairs
+    double last_gemm_ms = 0, last_gemm_flops = 0;
+    int64_t last_gemm_launches = 0;
+    double slice_flops = 0;
 };
 
 static bool g_configured = false;
@@ -71,7 +76,7 @@ extern "C" {
 
 void tob_default_options(tob_options* opt) {
     opt->device = 0;
-    opt->use_graph = 1;
+    opt->use_graph = 2;
     opt->kernel_policy = 0;
     opt->hoist_invariant = 1;
     opt->mem_limit_bytes = 0;
@@ -135,7 +140,10 @@ static void release_device(tob_plan* p) {
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
+    p->gemm_events.clear();
+    p->own_stream = nullptr;
     p->d_block = nullptr; p->d_state = nullptr; p->d_leaf_off = nullptr; p->d_term_start = nullptr;
     p->d_id_bit = nullptr; p->d_addr_bit = nullptr; p->h_state = nullptr; p->h_stage = nullptr;
     p->ev0 = p->ev1 = nullptr; p->stream = nullptr;
@@ -170,7 +178,10 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         set_error("plan needs " + std::to_string(need) + " bytes, device has " + std::to_string(free_b) + " free");
         return TOB_E_OOM;
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    p->stream = p->own_stream;
+    p->slice_flops = 0;
+    for (const Op& op : G.slice_ops) p->slice_flops += op.flops;
     CUDA_TRY(cudaEventCreate(&p->ev0));
     CUDA_TRY(cudaEventCreate(&p->ev1));
     const int64_t block = G.leaf_doubles + G.arena_doubles + G.ws_doubles + 32;
@@ -291,9 +302,36 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     p->h_state->pad = 0.0;
     CUDA_TRY(cudaMemcpyAsync(p->d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
+    const int ug = p->prog.opt.use_graph;
+    const bool as_graph = (ug == 1) || (ug == 2 && p->slice_flops < 2e9);
+    size_t n_gemm = 0;
+    double gemm_flops = 0;
+    // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py)
+    auto timed_op = [&](const Op& op) -> int {
+        if (op.kind != OP_GEMM || as_graph) {
+            CUDA_TRY(launch_op(p, op, &launches));
+            return TOB_OK;
+        }
+        if (p->gemm_events.size() < 2 * (n_gemm + 1)) {
+            cudaEvent_t a, b;
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            p->gemm_events.push_back(a);
+            p->gemm_events.push_back(b);
+        }
+        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm], p->stream));
+        CUDA_TRY(launch_op(p, op, &launches));
+        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm + 1], p->stream));
+        n_gemm++;
+        gemm_flops += op.flops;
+        return TOB_OK;
+    };
     if (count > 0) {
-        for (const Op& op : p->prog.invariant_ops) CUDA_TRY(launch_op(p, op, &launches));
-        if (p->prog.opt.use_graph) {
+        for (const Op& op : p->prog.invariant_ops) {
+            int rc2 = timed_op(op);
+            if (rc2 != TOB_OK) return rc2;
+        }
+        if (as_graph) {
             if (!p->graph_exec) {
                 int per_slice = 0;
                 CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
@@ -307,7 +345,17 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
             for (uint64_t s = 0; s < count; s++) CUDA_TRY(cudaGraphLaunch(p->graph_exec, p->stream));
             launches += (int)(p->graph_launches_per_slice * count);
         } else {
-            for (uint64_t s = 0; s < count; s++) CUDA_TRY(launch_slice(p, &launches));
+            for (uint64_t s = 0; s < count; s++) {
+                if (p->has_terms) {
+                    SliceTables t{p->d_term_start, p->d_id_bit, p->d_addr_bit, p->d_leaf_off, (int32_t)p->prog.leaves.size()};
+                    CUDA_TRY(launch_begin_slice(p->d_state, t, p->stream));
+                    launches++;
+                }
+                for (const Op& op : p->prog.slice_ops) {
+                    int rc2 = timed_op(op);
+                    if (rc2 != TOB_OK) return rc2;
+                }
+            }
         }
     }
     CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
@@ -317,7 +365,31 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
     p->last_ms = ms;
     p->last_launches = launches;
+    p->last_gemm_ms = 0;
+    for (size_t i = 0; i < n_gemm; i++) {
+        float g = 0;
+        CUDA_TRY(cudaEventElapsedTime(&g, p->gemm_events[2 * i], p->gemm_events[2 * i + 1]));
+        p->last_gemm_ms += g;
+    }
+    p->last_gemm_flops = gemm_flops;
+    p->last_gemm_launches = (int64_t)n_gemm;
     *result = p->h_state->acc;
+    return TOB_OK;
+}
+
+int tob_plan_last_gemm(const tob_plan* p, double* ms, double* flops, int64_t* launches) {
+    if (!p) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (ms) *ms = p->last_gemm_ms;
+    if (flops) *flops = p->last_gemm_flops;
+    if (launches) *launches = p->last_gemm_launches;
+    return TOB_OK;
+}
+
+int tob_plan_set_stream(tob_plan* p, void* stream) {
+    if (!p || !p->uploaded) { set_error("tob_plan_set_stream: plan is not uploaded"); return TOB_E_INVALID; }
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
+    p->stream = stream ? (cudaStream_t)stream : p->own_stream;
     return TOB_OK;
 }
 
