@@ -69,6 +69,9 @@ typedef struct {
     int32_t kernel_policy;   /* 0 auto, 1 force the generic kernel for every join (debug / parity)         */
     int32_t hoist_invariant; /* 1: compute slice-invariant subtrees once (default), 0: per slice           */
     int64_t mem_limit_bytes; /* 0: use free device memory; else refuse (TOB_E_OOM) plans needing more      */
+    int32_t use_microtree;   /* 1 (default): subtrees made only of tiny joins run inside ONE kernel launch  */
+                             /* (one CTA per subtree); 0: one launch per join                              */
+    int32_t reserved;
 } tob_options;
 
 void tob_default_options(tob_options* opt);

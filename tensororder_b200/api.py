@@ -43,7 +43,7 @@ class CompiledPlan:
     """Owns one `tob_plan` (device arena, leaf tensors, CUDA graph)."""
 
     def __init__(self, flat: FlatPlan, device: int = 0, use_graph=None, kernel_policy: int = 0,
-                 hoist_invariant: bool = True, mem_limit_bytes: int = 0):
+                 hoist_invariant: bool = True, mem_limit_bytes: int = 0, use_microtree: bool = True):
         self.flat = flat
         self._handle = c_void_p()
         desc = cabi.tob_plan_desc()
@@ -66,6 +66,7 @@ class CompiledPlan:
         opt.kernel_policy = kernel_policy
         opt.hoist_invariant = 1 if hoist_invariant else 0
         opt.mem_limit_bytes = int(mem_limit_bytes)
+        opt.use_microtree = 1 if use_microtree else 0
         rc = cabi.lib.tob_plan_create(byref(desc), byref(opt), byref(self._handle))
         if rc != cabi.TOB_OK:
             raise ValueError("tob_plan_create: " + cabi.last_error())
@@ -162,6 +163,7 @@ class B200API:
         self._use_graph = None  # library default: graph replay for launch-bound slices
         self._kernel_policy = 0
         self._hoist = True
+        self._microtree = True
         self._distributed = True
         self.last_stats = {}
 
@@ -181,6 +183,8 @@ class B200API:
             self._kernel_policy = int(value)
         elif key == "hoist_invariant":
             self._hoist = bool(value)
+        elif key == "use_microtree":
+            self._microtree = bool(value)
         elif key == "distributed":
             self._distributed = bool(value)
         else:
@@ -207,7 +211,8 @@ class B200API:
         flat = flatten_plan(execution_plan, self.create_tensor)
         rank, world = self._rank_world()
         compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
-                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist)
+                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
+                                use_microtree=self._microtree)
         try:
             t1 = time.perf_counter()
             compiled.upload()

@@ -36,6 +36,8 @@ class tob_options(ctypes.Structure):
         ("kernel_policy", c_int32),
         ("hoist_invariant", c_int32),
         ("mem_limit_bytes", c_int64),
+        ("use_microtree", c_int32),
+        ("reserved", c_int32),
     ]
 
 

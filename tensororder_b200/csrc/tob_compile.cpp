@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <set>
 #include <sstream>
@@ -41,9 +42,16 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
         op->tn_log2 = std::min(n, 7);
         int64_t tiles = (int64_t)1 << ((m - op->tm_log2) + (n - op->tn_log2));
         int ks = 0;
-        if (allow_splitk) {
-            // fill at least ~2 waves of CTAs; keep >= 8 k-steps (128 K elements) per split
-            while (tiles * ((int64_t)1 << ks) < 2 * kNumSMs && (k - ks) > 7) ks++;
+        if (allow_splitk && tiles < 8 * kNumSMs) {
+            // short grid: pick the power-of-two K split with the best wave efficiency (blocks / SMs
+            // rounded up), keeping >= 128 K elements per split; ties go to the smaller split
+            double best = -1.0;
+            for (int c = 0; (k - c) >= 7 && c <= 6; c++) {
+                const double blocks = (double)(tiles << c);
+                const double waves = blocks / kNumSMs;
+                const double eff = waves / std::ceil(waves) - 0.004 * c;
+                if (eff > best + 1e-9) { best = eff; ks = c; }
+            }
         }
         op->ksplit_log2 = ks;
         return;
@@ -233,19 +241,13 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     }
     P->leaf_doubles = leaf_top;
 
-    // ---- ops (post-order), hoisting, arena ----
+    // ---- ops (post-order), micro subtrees, hoisting, arena ----
     const bool hoist = opt.hoist_invariant && S > 0;
     Arena arena;
     int64_t ws_max = 0;
     std::vector<int64_t> size_of(N, 0);
-    std::vector<char> persistent(N, 0);
-    if (hoist) {
-        for (int i = 0; i < N; i++) {
-            const NodeInfo& X = P->nodes[i];
-            if (X.leaf < 0 && !X.slice_dependent && X.parent >= 0 && P->nodes[X.parent].slice_dependent) persistent[i] = 1;
-        }
-    }
-    auto emit = [&](int i, std::vector<Op>* list) {
+
+    auto build_op = [&](int i) {
         NodeInfo& X = P->nodes[i];
         NodeInfo& A = P->nodes[X.left];
         NodeInfo& B = P->nodes[X.right];
@@ -265,34 +267,135 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             std::swap(op.m, op.n);
             op.mask_m = ~mask & ((op.m + op.n) >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << (op.m + op.n)) - 1));
         }
-        op.invariant = X.slice_dependent ? 0 : 1;
-        choose_kernel(&op, opt.kernel_policy, true);
+        return op;
+    };
+
+    // micro-closed subtrees
+    std::vector<char> closed(N, 0), is_root(N, 0), eff_dep(N, 0);
+    std::vector<int32_t> subtree_nodes(N, 1);
+    for (int i = 0; i < N; i++) {
+        const NodeInfo& X = P->nodes[i];
+        eff_dep[i] = X.slice_dependent ? 1 : 0;
+        if (X.leaf >= 0) { closed[i] = 1; continue; }
+        subtree_nodes[i] = 1 + subtree_nodes[X.left] + subtree_nodes[X.right];
+        const int k = P->nodes[X.left].k_with_sibling;
+        const int m = (int)P->nodes[X.left].edges.size() - k, n = (int)P->nodes[X.right].edges.size() - k;
+        const bool tiny = (m + k <= 12 && n + k <= 12 && m + n <= 12 && m + n + k <= 15);
+        closed[i] = (opt.use_microtree && tiny && closed[X.left] && closed[X.right]) ? 1 : 0;
+    }
+    for (int i = 0; i < N; i++) {
+        const NodeInfo& X = P->nodes[i];
+        if (X.leaf >= 0 || !closed[i]) continue;
+        is_root[i] = (X.parent < 0 || !closed[X.parent]) ? 1 : 0;
+    }
+    // every join of a micro subtree runs in the phase of the subtree's root
+    for (int i = N - 1; i >= 0; i--) {
+        const NodeInfo& X = P->nodes[i];
+        if (X.leaf >= 0 || !closed[i]) continue;
+        if (!is_root[i]) eff_dep[i] = eff_dep[X.parent];
+    }
+    std::vector<char> persistent(N, 0);
+    if (hoist) {
+        for (int i = 0; i < N; i++) {
+            const NodeInfo& X = P->nodes[i];
+            if (X.leaf < 0 && !eff_dep[i] && X.parent >= 0 && eff_dep[X.parent]) persistent[i] = 1;
+        }
+    }
+
+    auto place = [&](Op& op, int i) {
+        NodeInfo& X = P->nodes[i];
         size_of[i] = (int64_t)1 << (op.m + op.n);
         op.c_offset = arena.alloc(size_of[i]);
-        if (op.ksplit_log2 > 0) {
-            op.ws_offset = 0;
-            ws_max = std::max(ws_max, round_up(size_of[i] << op.ksplit_log2, kAlign));
-        }
         X.where.space = 1;
         X.where.offset = op.c_offset;
         X.where.leaf = -1;
         X.where.node = i;
+        P->total_flops += op.flops;
+        P->total_bytes += op.bytes;
+    };
+    auto emit = [&](int i, std::vector<Op>* list) {
+        NodeInfo& X = P->nodes[i];
+        Op op = build_op(i);
+        op.invariant = eff_dep[i] ? 0 : 1;
+        choose_kernel(&op, opt.kernel_policy, true);
+        place(op, i);
+        if (op.ksplit_log2 > 0) {
+            op.ws_offset = 0;
+            ws_max = std::max(ws_max, round_up(size_of[i] << op.ksplit_log2, kAlign));
+        }
         for (int c : {X.left, X.right}) {
             const NodeInfo& Cn = P->nodes[c];
             if (Cn.leaf < 0 && !persistent[c]) arena.release(Cn.where.offset, size_of[c]);
         }
-        P->total_flops += op.flops;
-        P->total_bytes += op.bytes;
         list->push_back(op);
     };
+    auto run_phase = [&](int dep, std::vector<Op>* list, int which) {
+        // 1. all micro subtrees of this phase: one launch, one CTA per (packed) subtree
+        MicroProgram& mp = P->micro[which];
+        std::vector<std::vector<Op>> subtrees;
+        std::vector<double> work;
+        std::vector<std::pair<int64_t, int64_t>> deferred;  // arena space freed only after the launch
+        for (int r = 0; r < N; r++) {
+            if (!is_root[r] || eff_dep[r] != dep) continue;
+            subtrees.emplace_back();
+            work.push_back(0.0);
+            for (int i = r - subtree_nodes[r] + 1; i <= r; i++) {
+                NodeInfo& X = P->nodes[i];
+                if (X.leaf >= 0) continue;
+                Op op = build_op(i);
+                op.invariant = dep ? 0 : 1;
+                op.kind = OP_GENERIC;
+                op.threads_per_out = 1;
+                op.flops = 2.0 * std::ldexp(1.0, op.m + op.n + op.k);
+                op.bytes = 8.0 * (std::ldexp(1.0, op.m + op.k) + std::ldexp(1.0, op.n + op.k) + std::ldexp(1.0, op.m + op.n));
+                place(op, i);
+                for (int c : {X.left, X.right}) {
+                    const NodeInfo& Cn = P->nodes[c];
+                    if (Cn.leaf < 0 && !persistent[c]) deferred.emplace_back(Cn.where.offset, size_of[c]);
+                }
+                // cost model for packing: per-join latency floor + multiply-adds
+                work.back() += 2000.0 + std::ldexp(1.0, op.m + op.n + op.k);
+                subtrees.back().push_back(op);
+            }
+        }
+        if (!subtrees.empty()) {
+            const int n_cta = (int)std::min<size_t>(subtrees.size(), 2 * kNumSMs);
+            std::vector<size_t> order(subtrees.size());
+            for (size_t j = 0; j < order.size(); j++) order[j] = j;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return work[a] > work[b]; });
+            std::vector<std::vector<size_t>> bins(n_cta);
+            std::vector<double> load(n_cta, 0.0);
+            for (size_t j : order) {  // longest first onto the least loaded CTA
+                int best = 0;
+                for (int c = 1; c < n_cta; c++)
+                    if (load[c] < load[best]) best = c;
+                bins[best].push_back(j);
+                load[best] += work[j];
+            }
+            mp.cta_start.push_back(0);
+            for (int c = 0; c < n_cta; c++) {
+                for (size_t j : bins[c])
+                    for (const Op& op : subtrees[j]) mp.ops.push_back(op);
+                mp.cta_start.push_back((int32_t)mp.ops.size());
+            }
+            Op launch;
+            launch.kind = OP_MICRO;
+            launch.micro_which = which;
+            launch.invariant = dep ? 0 : 1;
+            for (const Op& op : mp.ops) { launch.flops += op.flops; launch.bytes += op.bytes; }
+            list->push_back(launch);
+            for (auto& d : deferred) arena.release(d.first, d.second);
+        }
+        // 2. the other joins of this phase, post-order
+        for (int i = 0; i < N; i++)
+            if (P->nodes[i].leaf < 0 && !closed[i] && eff_dep[i] == dep) emit(i, list);
+    };
     if (hoist) {
-        for (int i = 0; i < N; i++)
-            if (P->nodes[i].leaf < 0 && !P->nodes[i].slice_dependent) emit(i, &P->invariant_ops);
-        for (int i = 0; i < N; i++)
-            if (P->nodes[i].leaf < 0 && P->nodes[i].slice_dependent) emit(i, &P->slice_ops);
+        run_phase(0, &P->invariant_ops, 0);
+        run_phase(1, &P->slice_ops, 1);
     } else {
-        for (int i = 0; i < N; i++)
-            if (P->nodes[i].leaf < 0) emit(i, &P->slice_ops);
+        for (int i = 0; i < N; i++) eff_dep[i] = 1;
+        run_phase(1, &P->slice_ops, 1);
     }
     P->root = P->nodes[N - 1].where;
     Op acc;
@@ -312,11 +415,21 @@ std::string describe(const Program& P) {
     auto ref = [&](const OperandRef& r) {
         o << "{\"space\":" << r.space << ",\"offset\":" << r.offset << ",\"leaf\":" << r.leaf << ",\"node\":" << r.node << "}";
     };
-    auto ops = [&](const std::vector<Op>& v) {
+    std::function<void(const std::vector<Op>&)> ops = [&](const std::vector<Op>& v) {
         o << "[";
         for (size_t i = 0; i < v.size(); i++) {
             const Op& op = v[i];
             if (i) o << ",";
+            if (op.kind == OP_MICRO) {
+                const MicroProgram& mp = P.micro[op.micro_which];
+                o << "{\"kind\":3,\"which\":" << op.micro_which << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops
+                  << ",\"bytes\":" << op.bytes << ",\"cta_start\":[";
+                for (size_t j = 0; j < mp.cta_start.size(); j++) o << (j ? "," : "") << mp.cta_start[j];
+                o << "],\"micro\":";
+                ops(mp.ops);
+                o << "}";
+                continue;
+            }
             o << "{\"kind\":" << op.kind << ",\"node\":" << op.node << ",\"a\":";
             ref(op.a);
             o << ",\"b\":";

@@ -49,6 +49,8 @@ struct tob_plan {
     double last_gemm_ms = 0, last_gemm_flops = 0;
     int64_t last_gemm_launches = 0;
     double slice_flops = 0;
+    MicroOpDev* d_micro_ops[2] = {nullptr, nullptr};
+    int32_t* d_micro_start[2] = {nullptr, nullptr};
 };
 
 static bool g_configured = false;
@@ -80,6 +82,8 @@ void tob_default_options(tob_options* opt) {
     opt->kernel_policy = 0;
     opt->hoist_invariant = 1;
     opt->mem_limit_bytes = 0;
+    opt->use_microtree = 1;
+    opt->reserved = 0;
 }
 
 const char* tob_last_error(void) { return g_error.c_str(); }
@@ -140,6 +144,12 @@ static void release_device(tob_plan* p) {
     if (p->h_stage) cudaFreeHost(p->h_stage);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    for (int w = 0; w < 2; w++) {
+        if (p->d_micro_ops[w]) cudaFree(p->d_micro_ops[w]);
+        if (p->d_micro_start[w]) cudaFree(p->d_micro_start[w]);
+        p->d_micro_ops[w] = nullptr;
+        p->d_micro_start[w] = nullptr;
+    }
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
     p->gemm_events.clear();
@@ -215,6 +225,28 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         CUDA_TRY(cudaMemcpyAsync(p->d_id_bit, id_bit.data(), id_bit.size(), cudaMemcpyHostToDevice, p->stream));
         CUDA_TRY(cudaMemcpyAsync(p->d_addr_bit, addr_bit.data(), addr_bit.size(), cudaMemcpyHostToDevice, p->stream));
     }
+    // micro-subtree programs
+    std::vector<MicroOpDev> micro_host[2];
+    for (int w = 0; w < 2; w++) {
+        const MicroProgram& mp = G.micro[w];
+        if (mp.ops.empty()) continue;
+        for (const Op& op : mp.ops) {
+            MicroOpDev d;
+            memset(&d, 0, sizeof(d));
+            d.a_off = op.a.offset; d.b_off = op.b.offset; d.c_off = op.c_offset;
+            d.a_leaf = op.a.leaf; d.b_leaf = op.b.leaf;
+            d.mask_m = (uint16_t)op.mask_m;
+            d.a_space = (uint8_t)op.a.space; d.b_space = (uint8_t)op.b.space;
+            d.m = (uint8_t)op.m; d.n = (uint8_t)op.n; d.k = (uint8_t)op.k;
+            micro_host[w].push_back(d);
+        }
+        CUDA_TRY(cudaMalloc(&p->d_micro_ops[w], micro_host[w].size() * sizeof(MicroOpDev)));
+        CUDA_TRY(cudaMemcpyAsync(p->d_micro_ops[w], micro_host[w].data(), micro_host[w].size() * sizeof(MicroOpDev),
+                                 cudaMemcpyHostToDevice, p->stream));
+        CUDA_TRY(cudaMalloc(&p->d_micro_start[w], mp.cta_start.size() * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpyAsync(p->d_micro_start[w], mp.cta_start.data(), mp.cta_start.size() * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, p->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(p->stream));  // the std::vectors above die at scope exit
 
     // leaves: permute on the host into the canonical device layout, one H2D copy
@@ -265,6 +297,12 @@ static cudaError_t launch_op(tob_plan* p, const Op& op, int* launches) {
         const double* root = (op.a.space == 0 ? p->d_leaves : p->d_arena) + op.a.offset;
         (*launches)++;
         return launch_accum(p->d_state, root, p->d_leaf_off, op.a.leaf, p->stream);
+    }
+    if (op.kind == OP_MICRO) {
+        const int w = op.micro_which;
+        (*launches)++;
+        return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)p->prog.micro[w].cta_start.size() - 1,
+                                p->d_leaves, p->d_arena, p->d_leaf_off, p->stream);
     }
     KParams k = make_params(p, op);
     return launch_contract(op, k, p->stream, launches);

@@ -19,6 +19,7 @@ enum OpKind : int32_t {
     OP_GENERIC = 0,  // thread / warp / CTA per output element, bandwidth-bound
     OP_GEMM = 1,     // DMMA tile kernel, compute-bound
     OP_ACCUM = 2,    // acc += root scalar
+    OP_MICRO = 3,    // one launch executing every join of the tiny ("micro-closed") subtrees, one CTA per subtree
 };
 
 struct OperandRef {
@@ -42,7 +43,16 @@ struct Op {
     int32_t tm_log2 = 7, tn_log2 = 7;
     int64_t ws_offset = -1;     // workspace offset (doubles) for split-K partials
     int32_t invariant = 0;      // 1: independent of the slice id (hoisted)
+    int32_t micro_which = -1;   // OP_MICRO: index into Program::micro
     double flops = 0, bytes = 0;
+};
+
+// Tiny subtrees (every operand and result <= 2^12 doubles, <= 2^15 multiply-adds per join, closed under
+// descendants) depend only on leaves: all of them run in one launch, each subtree sequentially inside
+// one CTA with __syncthreads between its joins.
+struct MicroProgram {
+    std::vector<Op> ops;              // grouped by CTA, post-order inside a subtree
+    std::vector<int32_t> cta_start;   // [n_ctas + 1]
 };
 
 struct LeafInfo {
@@ -73,6 +83,7 @@ struct Program {
     std::vector<LeafInfo> leaves;
     std::vector<Op> invariant_ops;    // run once per tob_plan_run
     std::vector<Op> slice_ops;        // run once per slice
+    MicroProgram micro[2];            // [0] invariant phase, [1] slice phase
     int64_t leaf_doubles = 0;         // device leaf region
     int64_t arena_doubles = 0;        // intermediates
     int64_t ws_doubles = 0;           // split-K workspace

@@ -13,6 +13,7 @@
 //  * k_permute     — stand-alone index (address-bit) permutation through shared memory.
 //  * k_begin_slice / k_accum — slice bookkeeping kept on the device so a slice replays as a CUDA graph.
 #include <cstdio>
+#include <cstdlib>
 
 #include "tob_kernels.cuh"
 
@@ -194,19 +195,28 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-constexpr int GEMM_TK = 16;   // doubles per K step: one 128-byte line per tile row
-constexpr int GEMM_LDS = 20;  // shared-memory row stride in doubles (== 4 mod 16: conflict-free fragments)
+// K step per pipeline stage (doubles) and the padded shared-memory row stride: stride == 4 (mod 16)
+// makes the 8x4 DMMA fragment loads (LDS.64) conflict-free for both TK = 16 and TK = 32.
+template <int TK>
+struct GemmCfg {
+    static constexpr int LDS = TK + 4;
+    static constexpr int CHUNKS = TK / 2;        // 16-byte chunks per tile row
+    static constexpr int ROWS_PER_PASS = 256 / CHUNKS;
+};
 
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES>
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES>
 __global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int WTM = TM / WM, WTN = TN / WN;  // warp tile
     constexpr int MB = WTM / 8, NB = WTN / 8;    // 8x8 DMMA blocks per warp tile
+    constexpr int LDS = GemmCfg<TK>::LDS, CHUNKS = GemmCfg<TK>::CHUNKS, RPP = GemmCfg<TK>::ROWS_PER_PASS;
+    constexpr int K4 = TK / 4;
     static_assert(WM * WN == 8, "8 warps");
+    static_assert(TM % RPP == 0 && TN % RPP == 0, "loader passes");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
-    double* Bs = As + STAGES * TM * GEMM_LDS;
-    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * GEMM_LDS);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
     unsigned long long* cN = cM + TM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -228,24 +238,24 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
     const unsigned long long tile_m = gidx * group + (r % group), tile_n = r / group;
 
     const unsigned long long Ksplit = (1ull << k) >> ks;
-    const int KT = (int)(Ksplit / GEMM_TK);
+    const int KT = (int)(Ksplit / TK);
     const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
     const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
 
-    const int chunk = tid & 7, row0 = tid >> 3;
+    const int chunk = tid % CHUNKS, row0 = tid / CHUNKS;
+    const double* a_src = A + ((unsigned long long)row0 << k) + chunk * 2;
+    const double* b_src = B + ((unsigned long long)row0 << k) + chunk * 2;
+    const unsigned long long pass_stride = (unsigned long long)RPP << k;
+    const int dst_off = row0 * LDS + chunk * 2;
     auto load_stage = [&](int s, int kt) {
-        double* as = As + s * TM * GEMM_LDS;
-        double* bs = Bs + s * TN * GEMM_LDS;
+        double* as = As + s * TM * LDS + dst_off;
+        double* bs = Bs + s * TN * LDS + dst_off;
+        const double* ag = a_src + kt * TK;
+        const double* bg = b_src + kt * TK;
 #pragma unroll
-        for (int i = 0; i < TM / 32; i++) {
-            const int row = row0 + 32 * i;
-            cp_async16(as + row * GEMM_LDS + chunk * 2, A + ((unsigned long long)row << k) + kt * GEMM_TK + chunk * 2);
-        }
+        for (int i = 0; i < TM / RPP; i++) cp_async16(as + i * RPP * LDS, ag + i * pass_stride);
 #pragma unroll
-        for (int i = 0; i < TN / 32; i++) {
-            const int row = row0 + 32 * i;
-            cp_async16(bs + row * GEMM_LDS + chunk * 2, B + ((unsigned long long)row << k) + kt * GEMM_TK + chunk * 2);
-        }
+        for (int i = 0; i < TN / RPP; i++) cp_async16(bs + i * RPP * LDS, bg + i * pass_stride);
     };
 
     double acc[MB][NB][2];
@@ -259,25 +269,34 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
         if (s < KT) load_stage(s, s);
         cp_async_commit();
     }
+    const int frag_off_a = (wm * WTM + g) * LDS + t;
+    const int frag_off_b = (wn * WTN + g) * LDS + t;
+    double af[2][MB], bf[2][NB];  // register double buffer: fragments of step k4+1 load while k4 computes
     for (int kt = 0; kt < KT; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         const int nk = kt + STAGES - 1;
         if (nk < KT) load_stage(nk % STAGES, nk);
         cp_async_commit();
-        const double* as = As + (kt % STAGES) * TM * GEMM_LDS + (wm * WTM + g) * GEMM_LDS + t;
-        const double* bs = Bs + (kt % STAGES) * TN * GEMM_LDS + (wn * WTN + g) * GEMM_LDS + t;
+        const double* as = As + (kt % STAGES) * TM * LDS + frag_off_a;
+        const double* bs = Bs + (kt % STAGES) * TN * LDS + frag_off_b;
 #pragma unroll
-        for (int k4 = 0; k4 < GEMM_TK / 4; k4++) {
-            double af[MB], bf[NB];
+        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS];
 #pragma unroll
-            for (int i = 0; i < MB; i++) af[i] = as[i * 8 * GEMM_LDS + k4 * 4];
+        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS];
 #pragma unroll
-            for (int j = 0; j < NB; j++) bf[j] = bs[j * 8 * GEMM_LDS + k4 * 4];
+        for (int k4 = 0; k4 < K4; k4++) {
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < K4) {
+#pragma unroll
+                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + (k4 + 1) * 4];
+#pragma unroll
+                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + (k4 + 1) * 4];
+            }
 #pragma unroll
             for (int i = 0; i < MB; i++)
 #pragma unroll
-                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
     }
     cp_async_wait<0>();
@@ -302,22 +321,35 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
     }
 }
 
-template <int TM_LOG2, int TN_LOG2, int STAGES>
+template <int TM_LOG2, int TN_LOG2, int TK, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * GEMM_LDS * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
+    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (TK + 4) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
 }
 
-#define GEMM_77 k_gemm_dmma<7, 7, 2, 4, 4>
-#define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 4>
-#define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 4>
+// variant table: [0] = 128x128 TK16x4 stages, [1] = 128x128 TK32x3 stages (fewer CTA barriers per flop)
+#define GEMM_77_A k_gemm_dmma<7, 7, 2, 4, 16, 4>
+#define GEMM_77_B k_gemm_dmma<7, 7, 2, 4, 32, 3>
+#define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 4>
+#define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4>
+
+static int g_gemm_variant = -1;
+static int gemm_variant() {
+    if (g_gemm_variant < 0) {
+        const char* e = getenv("TOB_GEMM_VARIANT");
+        g_gemm_variant = e ? atoi(e) : 1;
+    }
+    return g_gemm_variant;
+}
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(GEMM_77, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 4>());
+    e = cudaFuncSetAttribute(GEMM_77_A, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 16, 4>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 4>());
+    e = cudaFuncSetAttribute(GEMM_77_B, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 32, 3>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 4>());
+    e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     return e;
 }
 
@@ -354,6 +386,59 @@ cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf
 }
 
 // ------------------------------------------------------------------------------------------------
+// micro subtrees: CTA b runs joins [cta_start[b], cta_start[b+1]) one after the other; every join is
+// tiny (<= 2^12 outputs, <= 2^15 multiply-adds), its operands were produced by this CTA or are leaves,
+// so a __syncthreads between joins is the only synchronisation.  Replaces hundreds of launch-bound
+// kernel launches per slice by one.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
+                                                   const double* leaves, double* arena, const long long* leaf_off) {
+    const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
+    for (int i = first; i < last; i++) {
+        const MicroOpDev op = ops[i];
+        const double* A = (op.a_space ? arena : leaves) + op.a_off + (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
+        const double* B = (op.b_space ? arena : leaves) + op.b_off + (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
+        double* C = arena + op.c_off;
+        const int tot = op.m + op.n, k = op.k;
+        const unsigned outs = 1u << tot;
+        const unsigned mask = op.mask_m;
+        for (unsigned c = threadIdx.x; c < outs; c += 256) {
+            unsigned mi = 0, ni = 0, im = 0, in = 0;
+            for (int b = 0; b < tot; b++) {
+                const unsigned bit = (c >> b) & 1u;
+                if ((mask >> b) & 1u) { mi |= bit << im; im++; }
+                else { ni |= bit << in; in++; }
+            }
+            const double* ar = A + ((size_t)mi << k);
+            const double* br = B + ((size_t)ni << k);
+            double s;
+            if (k == 0) {
+                s = ar[0] * br[0];
+            } else {
+                const double2* a2 = reinterpret_cast<const double2*>(ar);
+                const double2* b2 = reinterpret_cast<const double2*>(br);
+                const int K2 = 1 << (k - 1);
+                double s0 = 0.0, s1 = 0.0;
+                for (int j = 0; j < K2; j++) {
+                    const double2 x = a2[j], y = b2[j];
+                    s0 = fma(x.x, y.x, s0);
+                    s1 = fma(x.y, y.y, s1);
+                }
+                s = s0 + s1;
+            }
+            C[c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
+                             double* arena, const long long* leaf_off, cudaStream_t stream) {
+    k_microtree<<<n_ctas, 256, 0, stream>>>(ops, cta_start, leaves, arena, leaf_off);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // contract launcher
 // ------------------------------------------------------------------------------------------------
 static unsigned grid_for(unsigned long long items, unsigned long long per_block, unsigned long long cap) {
@@ -370,12 +455,16 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         const unsigned long long tiles = 1ull << ((op.m - op.tm_log2) + (op.n - op.tn_log2));
         const unsigned long long blocks = tiles << op.ksplit_log2;
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        if (op.tm_log2 == 7 && op.tn_log2 == 7)
-            GEMM_77<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 4>(), stream>>>(p);
-        else if (op.tm_log2 == 7 && op.tn_log2 == 6)
-            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 4>(), stream>>>(p);
+        if (op.tm_log2 == 7 && op.tn_log2 == 7) {
+            // the TK=32 variant needs K per split >= 32
+            if (gemm_variant() == 1 && (op.k - op.ksplit_log2) >= 5)
+                GEMM_77_B<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
+            else
+                GEMM_77_A<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 16, 4>(), stream>>>(p);
+        } else if (op.tm_log2 == 7 && op.tn_log2 == 6)
+            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 4>(), stream>>>(p);
         else if (op.tm_log2 == 6 && op.tn_log2 == 6)
-            GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 4>(), stream>>>(p);
+            GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
         else
             return cudaErrorInvalidConfiguration;
         (*launches)++;

@@ -29,6 +29,15 @@ struct KParams {
     BitRuns runs_m, runs_n;
 };
 
+// One join of a micro subtree (device copy).  m + n <= 12, operands <= 2^12 doubles.
+struct MicroOpDev {
+    long long a_off, b_off, c_off;  // doubles: a/b inside their space, c inside the arena
+    int32_t a_leaf, b_leaf;         // leaf_off index or -1
+    uint16_t mask_m;
+    uint8_t a_space, b_space;       // 0 leaves, 1 arena
+    uint8_t m, n, k, pad;
+};
+
 struct DevState {
     unsigned long long next_slice;
     unsigned long long stride;
@@ -58,6 +67,8 @@ struct PermuteParams {
 };
 
 cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
+                             double* arena, const long long* leaf_off, cudaStream_t stream);
 cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, cudaStream_t stream);
 cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream);
 cudaError_t launch_permute(const double* in, double* out, int rank, const int32_t* src_bit, cudaStream_t stream);

@@ -61,6 +61,12 @@ def run_program(desc, flat, first=0, count=None, stride=1):
         if op["kind"] == 2:
             acc += operand(op["a"], 1)[0]
             return
+        if op["kind"] == 3:  # micro-subtree launch: every join of every CTA, in CTA order
+            assert op["cta_start"][0] == 0 and op["cta_start"][-1] == len(op["micro"])
+            for sub in op["micro"]:
+                assert sub["m"] + sub["n"] <= 12 and sub["m"] + sub["k"] <= 12 and sub["n"] + sub["k"] <= 12
+                do(sub)
+            return
         m, n, k = op["m"], op["n"], op["k"]
         A = operand(op["a"], 1 << (m + k)).reshape(1 << m, 1 << k)
         B = operand(op["b"], 1 << (n + k)).reshape(1 << n, 1 << k)

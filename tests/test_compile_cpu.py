@@ -97,7 +97,29 @@ def test_forced_generic_policy_and_gemm_selection():
             assert op["m"] >= op["n"] >= 6 and op["k"] >= 4
             assert op["k"] - op["ksplit_log2"] >= 7 or op["ksplit_log2"] == 0
     forced = CompiledPlan(flat, kernel_policy=1).describe()
-    assert all(op["kind"] in (0, 2) for op in forced["slice_ops"])
+    assert all(op["kind"] in (0, 2, 3) for op in forced["slice_ops"])
+
+
+@pytest.mark.parametrize("name,variant", [("vc50_lineflow", None), ("vc100_lineflow", "min4"), ("vc150_lineflow", None)])
+def test_micro_subtrees(name, variant):
+    """Tiny subtrees collapse into one launch per phase; results are unchanged with the feature off."""
+    pp = load_golden(name)
+    if variant:
+        pp = pp.variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    on = CompiledPlan(flat).describe()
+    off = CompiledPlan(flat, use_microtree=False).describe()
+    n_joins = sum(1 for n in pp.postorder if len(n) == 2)
+    assert sum(1 for op in off["slice_ops"] + off["invariant_ops"] if op["kind"] in (0, 1)) == n_joins
+    micro = [op for op in on["slice_ops"] + on["invariant_ops"] if op["kind"] == 3]
+    assert 1 <= len(micro) <= 2
+    in_micro = sum(len(op["micro"]) for op in micro)
+    rest = sum(1 for op in on["slice_ops"] + on["invariant_ops"] if op["kind"] in (0, 1))
+    assert in_micro + rest == n_joins and in_micro > n_joins // 3
+    for op in micro:
+        assert op["cta_start"] == sorted(op["cta_start"]) and len(op["cta_start"]) - 1 <= 2 * 148
+    a, b = run_program(on, flat), run_program(off, flat)
+    assert math.isclose(a, b, rel_tol=1e-12) and math.isclose(a, pp.expected["count"], rel_tol=1e-12)
 
 
 def test_plan_errors():

@@ -112,6 +112,18 @@ def test_large_instances_slicing_invariance(name):
         assert math.isclose(got, base, rel_tol=REL), (v["name"], got, base)
 
 
+@pytest.mark.parametrize("name", ["vc50_lineflow", "vc120_lineflow", "vc150_mcc_factorflow", "toy_unit_neg_lineflow"])
+def test_microtree_kernel_matches_per_join_launches(name):
+    pp = load_golden(name)
+    on = _api(use_microtree=True)
+    off = _api(use_microtree=False)
+    a = on.contract_sliced(pp.as_execution_plan())
+    b = off.contract_sliced(pp.as_execution_plan())
+    assert math.isclose(float(a), float(b), rel_tol=1e-12)
+    _check(a, pp.expected)
+    assert on.last_stats["launches"] < off.last_stats["launches"]
+
+
 def test_contract_single_network_entry():
     pp = load_golden("vc50_factorflow")
     plan = pp.as_execution_plan()
