@@ -208,7 +208,7 @@ class B200API:
     # ---- the primary entry (base_api.py:17-28, called from execution.py:136) ----
     def contract_sliced(self, execution_plan, num_slice_limit=None):
         t0 = time.perf_counter()
-        flat = flatten_plan(execution_plan, self.create_tensor)
+        flat = flatten_plan(execution_plan)  # leaves are built through a buffer-backed create_tensor
         rank, world = self._rank_world()
         compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
                                 kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,

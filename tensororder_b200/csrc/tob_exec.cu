@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,32 +29,140 @@ struct tob_plan {
     Program prog;
     bool uploaded = false;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream runs are issued on (own or caller's)
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double* d_block = nullptr;  // [leaves | arena | workspace]
+    // one device block: [state | leaf_off | slice tables | micro programs | leaves | arena | workspace]
+    void* d_block = nullptr;
+    size_t d_block_size = 0;
     double *d_leaves = nullptr, *d_arena = nullptr, *d_ws = nullptr;
     DevState* d_state = nullptr;
     long long* d_leaf_off = nullptr;
     int32_t* d_term_start = nullptr;
     uint8_t *d_id_bit = nullptr, *d_addr_bit = nullptr;
-    DevState* h_state = nullptr;  // pinned
-    double* h_stage = nullptr;    // pinned leaf staging
+    MicroOpDev* d_micro_ops[2] = {nullptr, nullptr};
+    int32_t* d_micro_start[2] = {nullptr, nullptr};
+    // one pinned block mirroring the prefix of the device block up to the end of the leaves
+    void* h_block = nullptr;
+    size_t h_block_size = 0;
+    DevState* h_state = nullptr;     // upload slot
+    DevState* h_readback = nullptr;  // result slot
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool has_terms = false;
     double last_ms = 0;
     int64_t last_launches = 0;
     int64_t graph_launches_per_slice = 0;
-    cudaStream_t own_stream = nullptr;
+    int64_t runs = 0;
     std::vector<cudaEvent_t> gemm_events;  // pairs
     double last_gemm_ms = 0, last_gemm_flops = 0;
     int64_t last_gemm_launches = 0;
     double slice_flops = 0;
-    MicroOpDev* d_micro_ops[2] = {nullptr, nullptr};
-    int32_t* d_micro_start[2] = {nullptr, nullptr};
 };
 
 static bool g_configured = false;
+
+// ------------------------------------------------------------------------------------------------
+// Process-wide caches.  A call of B200API.contract_sliced creates, uploads, runs and destroys a plan;
+// cudaMalloc / cudaMallocHost / cudaFree / stream + event creation cost milliseconds, more than the
+// kernels of a small instance.  Blocks and streams are therefore recycled (device blocks above
+// 2 GiB are returned to the driver at once; at most 8 GiB stay cached per device).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Block { void* ptr; size_t size; int device; bool pinned; };
+struct StreamSet { cudaStream_t stream; cudaEvent_t ev0, ev1; int device; };
+std::mutex g_pool_mu;
+std::vector<Block> g_free_blocks;
+std::vector<StreamSet> g_free_streams;
+const size_t kMaxCachedBlock = (size_t)2 << 30;
+const size_t kMaxCachedTotal = (size_t)8 << 30;
+
+void pool_trim_locked(int device, size_t keep_bytes) {
+    size_t total = 0;
+    for (const Block& b : g_free_blocks)
+        if (!b.pinned && b.device == device) total += b.size;
+    while (total > keep_bytes) {
+        int big = -1;
+        for (size_t i = 0; i < g_free_blocks.size(); i++)
+            if (!g_free_blocks[i].pinned && g_free_blocks[i].device == device &&
+                (big < 0 || g_free_blocks[i].size > g_free_blocks[big].size)) big = (int)i;
+        if (big < 0) break;
+        cudaFree(g_free_blocks[big].ptr);
+        total -= g_free_blocks[big].size;
+        g_free_blocks.erase(g_free_blocks.begin() + big);
+    }
+}
+
+cudaError_t pool_acquire(size_t bytes, int device, bool pinned, Block* out) {
+    bytes = (bytes + 4095) / 4096 * 4096;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_free_blocks.size(); i++) {
+            const Block& b = g_free_blocks[i];
+            if (b.pinned != pinned || (!pinned && b.device != device) || b.size < bytes) continue;
+            if (b.size > 4 * bytes + ((size_t)64 << 20)) continue;  // do not burn a huge block on a tiny plan
+            if (best < 0 || b.size < g_free_blocks[best].size) best = (int)i;
+        }
+        if (best >= 0) {
+            *out = g_free_blocks[best];
+            g_free_blocks.erase(g_free_blocks.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    void* ptr = nullptr;
+    cudaError_t e = pinned ? cudaMallocHost(&ptr, bytes) : cudaMalloc(&ptr, bytes);
+    if (e == cudaErrorMemoryAllocation && !pinned) {
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lock(g_pool_mu);
+            pool_trim_locked(device, 0);
+        }
+        e = cudaMalloc(&ptr, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    *out = Block{ptr, bytes, device, pinned};
+    return cudaSuccess;
+}
+
+void pool_release(const Block& b) {
+    if (!b.ptr) return;
+    if (!b.pinned && b.size > kMaxCachedBlock) {
+        cudaFree(b.ptr);
+        return;
+    }
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    g_free_blocks.push_back(b);
+    if (!b.pinned) pool_trim_locked(b.device, kMaxCachedTotal);
+}
+
+cudaError_t streams_acquire(int device, StreamSet* out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (size_t i = 0; i < g_free_streams.size(); i++)
+            if (g_free_streams[i].device == device) {
+                *out = g_free_streams[i];
+                g_free_streams.erase(g_free_streams.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    StreamSet s{nullptr, nullptr, nullptr, device};
+    cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
+    if (e != cudaSuccess) return e;
+    *out = s;
+    return cudaSuccess;
+}
+
+void streams_release(const StreamSet& s) {
+    if (!s.stream) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    g_free_streams.push_back(s);
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
 
 static int ensure_device(int device) {
     int n = 0;
@@ -112,7 +221,10 @@ int tob_plan_create(const tob_plan_desc* desc, const tob_options* opt, tob_plan*
 }
 
 int64_t tob_plan_peak_bytes(const tob_plan* p) {
-    return 8 * (p->prog.leaf_doubles + p->prog.arena_doubles + p->prog.ws_doubles) + 4096;
+    size_t tables = 4096 + 32 * p->prog.leaves.size();
+    for (int w = 0; w < 2; w++) tables += p->prog.micro[w].ops.size() * sizeof(MicroOpDev) + p->prog.micro[w].cta_start.size() * 4 + 1024;
+    for (const LeafInfo& L : p->prog.leaves) tables += 2 * L.slice_id_bit.size();
+    return 8 * (p->prog.leaf_doubles + p->prog.arena_doubles + p->prog.ws_doubles) + (int64_t)tables;
 }
 
 uint64_t tob_plan_num_slices(const tob_plan* p) { return (uint64_t)1 << p->prog.n_slice_groups; }
@@ -130,39 +242,28 @@ int64_t tob_plan_describe(const tob_plan* p, char* buf, int64_t cap) {
 int64_t tob_plan_num_ops(const tob_plan* p) { return (int64_t)(p->prog.invariant_ops.size() + p->prog.slice_ops.size()); }
 
 static void release_device(tob_plan* p) {
+    if (p->own_stream) cudaStreamSynchronize(p->own_stream);
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
     p->graph_exec = nullptr;
     p->graph = nullptr;
-    if (p->d_block) cudaFree(p->d_block);
-    if (p->d_state) cudaFree(p->d_state);
-    if (p->d_leaf_off) cudaFree(p->d_leaf_off);
-    if (p->d_term_start) cudaFree(p->d_term_start);
-    if (p->d_id_bit) cudaFree(p->d_id_bit);
-    if (p->d_addr_bit) cudaFree(p->d_addr_bit);
-    if (p->h_state) cudaFreeHost(p->h_state);
-    if (p->h_stage) cudaFreeHost(p->h_stage);
-    if (p->ev0) cudaEventDestroy(p->ev0);
-    if (p->ev1) cudaEventDestroy(p->ev1);
-    for (int w = 0; w < 2; w++) {
-        if (p->d_micro_ops[w]) cudaFree(p->d_micro_ops[w]);
-        if (p->d_micro_start[w]) cudaFree(p->d_micro_start[w]);
-        p->d_micro_ops[w] = nullptr;
-        p->d_micro_start[w] = nullptr;
-    }
-    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    pool_release(Block{p->d_block, p->d_block_size, p->device, false});
+    pool_release(Block{p->h_block, p->h_block_size, p->device, true});
+    streams_release(StreamSet{p->own_stream, p->ev0, p->ev1, p->device});
     for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
     p->gemm_events.clear();
-    p->own_stream = nullptr;
-    p->d_block = nullptr; p->d_state = nullptr; p->d_leaf_off = nullptr; p->d_term_start = nullptr;
-    p->d_id_bit = nullptr; p->d_addr_bit = nullptr; p->h_state = nullptr; p->h_stage = nullptr;
-    p->ev0 = p->ev1 = nullptr; p->stream = nullptr;
+    p->d_block = nullptr; p->h_block = nullptr; p->d_state = nullptr; p->d_leaf_off = nullptr;
+    p->d_term_start = nullptr; p->d_id_bit = nullptr; p->d_addr_bit = nullptr;
+    p->h_state = nullptr; p->h_readback = nullptr;
+    for (int w = 0; w < 2; w++) { p->d_micro_ops[w] = nullptr; p->d_micro_start[w] = nullptr; }
+    p->own_stream = nullptr; p->ev0 = p->ev1 = nullptr; p->stream = nullptr;
     p->uploaded = false;
+    p->runs = 0;
 }
 
 void tob_plan_destroy(tob_plan* p) {
     if (!p) return;
-    if (p->uploaded || p->stream) {
+    if (p->uploaded || p->own_stream) {
         cudaSetDevice(p->device);
         release_device(p);
     }
@@ -175,7 +276,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     if (n_doubles != G.src_leaf_len) { set_error("leaf buffer length does not match the plan"); return TOB_E_INVALID; }
     int rc = ensure_device(p->device);
     if (rc != TOB_OK) return rc;
-    if (p->uploaded || p->stream) release_device(p);
+    if (p->uploaded || p->own_stream) release_device(p);
 
     const int64_t need = tob_plan_peak_bytes(p);
     if (G.opt.mem_limit_bytes > 0 && need > G.opt.mem_limit_bytes) {
@@ -188,21 +289,16 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         set_error("plan needs " + std::to_string(need) + " bytes, device has " + std::to_string(free_b) + " free");
         return TOB_E_OOM;
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
-    p->stream = p->own_stream;
+    StreamSet ss;
+    CUDA_TRY(streams_acquire(p->device, &ss));
+    p->own_stream = ss.stream;
+    p->stream = ss.stream;
+    p->ev0 = ss.ev0;
+    p->ev1 = ss.ev1;
     p->slice_flops = 0;
     for (const Op& op : G.slice_ops) p->slice_flops += op.flops;
-    CUDA_TRY(cudaEventCreate(&p->ev0));
-    CUDA_TRY(cudaEventCreate(&p->ev1));
-    const int64_t block = G.leaf_doubles + G.arena_doubles + G.ws_doubles + 32;
-    CUDA_TRY(cudaMalloc(&p->d_block, (size_t)block * 8));
-    p->d_leaves = p->d_block;
-    p->d_arena = p->d_block + G.leaf_doubles;
-    p->d_ws = p->d_arena + G.arena_doubles;
-    CUDA_TRY(cudaMalloc(&p->d_state, sizeof(DevState)));
-    CUDA_TRY(cudaMallocHost(&p->h_state, sizeof(DevState)));
 
-    // slice term tables
+    // ---- host-side tables ----
     const int L = (int)G.leaves.size();
     std::vector<int32_t> term_start(L + 1, 0);
     std::vector<uint8_t> id_bit, addr_bit;
@@ -215,55 +311,87 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     }
     term_start[L] = (int32_t)id_bit.size();
     p->has_terms = !id_bit.empty();
-    CUDA_TRY(cudaMalloc(&p->d_leaf_off, sizeof(long long) * (L + 1)));
-    CUDA_TRY(cudaMemsetAsync(p->d_leaf_off, 0, sizeof(long long) * (L + 1), p->stream));
-    CUDA_TRY(cudaMalloc(&p->d_term_start, sizeof(int32_t) * (L + 1)));
-    CUDA_TRY(cudaMemcpyAsync(p->d_term_start, term_start.data(), sizeof(int32_t) * (L + 1), cudaMemcpyHostToDevice, p->stream));
-    CUDA_TRY(cudaMalloc(&p->d_id_bit, id_bit.size() + 1));
-    CUDA_TRY(cudaMalloc(&p->d_addr_bit, addr_bit.size() + 1));
-    if (!id_bit.empty()) {
-        CUDA_TRY(cudaMemcpyAsync(p->d_id_bit, id_bit.data(), id_bit.size(), cudaMemcpyHostToDevice, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(p->d_addr_bit, addr_bit.data(), addr_bit.size(), cudaMemcpyHostToDevice, p->stream));
+
+    // ---- layout of the single device block (byte offsets, 256-B aligned sections) ----
+    size_t off = 0;
+    auto section = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_state = section(sizeof(DevState));
+    const size_t o_leaf_off = section(sizeof(long long) * (L + 1));
+    const size_t o_term = section(sizeof(int32_t) * (L + 1));
+    const size_t o_idb = section(id_bit.size() + 1);
+    const size_t o_adb = section(addr_bit.size() + 1);
+    size_t o_mops[2], o_mstart[2];
+    for (int w = 0; w < 2; w++) {
+        o_mops[w] = section(G.micro[w].ops.size() * sizeof(MicroOpDev) + 8);
+        o_mstart[w] = section(G.micro[w].cta_start.size() * sizeof(int32_t) + 8);
     }
-    // micro-subtree programs
-    std::vector<MicroOpDev> micro_host[2];
+    const size_t o_leaves = section((size_t)G.leaf_doubles * 8);
+    const size_t prefix_bytes = off;  // everything up to here is initialised from the pinned mirror
+    const size_t o_arena = section((size_t)G.arena_doubles * 8);
+    const size_t o_ws = section((size_t)G.ws_doubles * 8);
+    const size_t total_bytes = off + 256;
+
+    Block db, hb;
+    CUDA_TRY(pool_acquire(total_bytes, p->device, false, &db));
+    p->d_block = db.ptr;
+    p->d_block_size = db.size;
+    CUDA_TRY(pool_acquire(prefix_bytes + 256, p->device, true, &hb));
+    p->h_block = hb.ptr;
+    p->h_block_size = hb.size;
+    char* d = static_cast<char*>(p->d_block);
+    char* h = static_cast<char*>(p->h_block);
+    p->d_state = reinterpret_cast<DevState*>(d + o_state);
+    p->d_leaf_off = reinterpret_cast<long long*>(d + o_leaf_off);
+    p->d_term_start = reinterpret_cast<int32_t*>(d + o_term);
+    p->d_id_bit = reinterpret_cast<uint8_t*>(d + o_idb);
+    p->d_addr_bit = reinterpret_cast<uint8_t*>(d + o_adb);
+    for (int w = 0; w < 2; w++) {
+        p->d_micro_ops[w] = reinterpret_cast<MicroOpDev*>(d + o_mops[w]);
+        p->d_micro_start[w] = reinterpret_cast<int32_t*>(d + o_mstart[w]);
+    }
+    p->d_leaves = reinterpret_cast<double*>(d + o_leaves);
+    p->d_arena = reinterpret_cast<double*>(d + o_arena);
+    p->d_ws = reinterpret_cast<double*>(d + o_ws);
+    p->h_state = reinterpret_cast<DevState*>(h + o_state);
+    p->h_readback = reinterpret_cast<DevState*>(h + prefix_bytes);
+
+    // ---- fill the pinned mirror: tables, micro programs, leaves permuted into canonical order ----
+    memset(h, 0, o_leaves);
+    memcpy(h + o_term, term_start.data(), sizeof(int32_t) * (L + 1));
+    if (!id_bit.empty()) {
+        memcpy(h + o_idb, id_bit.data(), id_bit.size());
+        memcpy(h + o_adb, addr_bit.data(), addr_bit.size());
+    }
     for (int w = 0; w < 2; w++) {
         const MicroProgram& mp = G.micro[w];
-        if (mp.ops.empty()) continue;
-        for (const Op& op : mp.ops) {
-            MicroOpDev d;
-            memset(&d, 0, sizeof(d));
-            d.a_off = op.a.offset; d.b_off = op.b.offset; d.c_off = op.c_offset;
-            d.a_leaf = op.a.leaf; d.b_leaf = op.b.leaf;
-            d.mask_m = (uint16_t)op.mask_m;
-            d.a_space = (uint8_t)op.a.space; d.b_space = (uint8_t)op.b.space;
-            d.m = (uint8_t)op.m; d.n = (uint8_t)op.n; d.k = (uint8_t)op.k;
-            micro_host[w].push_back(d);
+        MicroOpDev* mo = reinterpret_cast<MicroOpDev*>(h + o_mops[w]);
+        for (size_t j = 0; j < mp.ops.size(); j++) {
+            const Op& op = mp.ops[j];
+            MicroOpDev m;
+            memset(&m, 0, sizeof(m));
+            m.a_off = op.a.offset; m.b_off = op.b.offset; m.c_off = op.c_offset;
+            m.a_leaf = op.a.leaf; m.b_leaf = op.b.leaf;
+            m.mask_m = (uint16_t)op.mask_m;
+            m.a_space = (uint8_t)op.a.space; m.b_space = (uint8_t)op.b.space;
+            m.m = (uint8_t)op.m; m.n = (uint8_t)op.n; m.k = (uint8_t)op.k;
+            mo[j] = m;
         }
-        CUDA_TRY(cudaMalloc(&p->d_micro_ops[w], micro_host[w].size() * sizeof(MicroOpDev)));
-        CUDA_TRY(cudaMemcpyAsync(p->d_micro_ops[w], micro_host[w].data(), micro_host[w].size() * sizeof(MicroOpDev),
-                                 cudaMemcpyHostToDevice, p->stream));
-        CUDA_TRY(cudaMalloc(&p->d_micro_start[w], mp.cta_start.size() * sizeof(int32_t)));
-        CUDA_TRY(cudaMemcpyAsync(p->d_micro_start[w], mp.cta_start.data(), mp.cta_start.size() * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, p->stream));
+        if (!mp.cta_start.empty()) memcpy(h + o_mstart[w], mp.cta_start.data(), mp.cta_start.size() * sizeof(int32_t));
     }
-    CUDA_TRY(cudaStreamSynchronize(p->stream));  // the std::vectors above die at scope exit
-
-    // leaves: permute on the host into the canonical device layout, one H2D copy
-    CUDA_TRY(cudaMallocHost(&p->h_stage, (size_t)std::max<int64_t>(G.leaf_doubles, 1) * 8));
-    memset(p->h_stage, 0, (size_t)G.leaf_doubles * 8);
+    double* h_leaves = reinterpret_cast<double*>(h + o_leaves);
     for (const LeafInfo& Lf : G.leaves) {
         const int64_t n = (int64_t)1 << Lf.rank;
         const double* src = leaf_data + Lf.src_offset;
-        double* dst = p->h_stage + Lf.dev_offset;
-        for (int64_t d = 0; d < n; d++) {
-            int64_t s = 0;
-            for (int q = 0; q < Lf.rank; q++) s |= ((d >> q) & 1) << Lf.src_bit[q];
-            dst[d] = src[s];
+        double* dst = h_leaves + Lf.dev_offset;
+        for (int64_t e = 0; e < n; e++) {
+            int64_t sidx = 0;
+            for (int q = 0; q < Lf.rank; q++) sidx |= ((e >> q) & 1) << Lf.src_bit[q];
+            dst[e] = src[sidx];
         }
+        for (int64_t e = n; e < (int64_t)align_up((size_t)n, 32); e++) dst[e] = 0.0;
     }
-    if (G.leaf_doubles > 0)
-        CUDA_TRY(cudaMemcpyAsync(p->d_leaves, p->h_stage, (size_t)G.leaf_doubles * 8, cudaMemcpyHostToDevice, p->stream));
+    // ---- ONE pinned host->device copy: state, tables, micro programs, leaves ----
+    CUDA_TRY(cudaMemcpyAsync(p->d_block, p->h_block, prefix_bytes, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->uploaded = true;
     return TOB_OK;
@@ -341,7 +469,9 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     CUDA_TRY(cudaMemcpyAsync(p->d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
     const int ug = p->prog.opt.use_graph;
-    const bool as_graph = (ug == 1) || (ug == 2 && p->slice_flops < 2e9);
+    // auto: launch-bound slices replay as a graph, but only once the plan is being reused (second run or
+    // several slices): a plan that runs a single slice once never pays capture + instantiate
+    const bool as_graph = (ug == 1) || (ug == 2 && p->slice_flops < 2e9 && (p->runs > 0 || count >= 4));
     size_t n_gemm = 0;
     double gemm_flops = 0;
     // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py)
@@ -397,7 +527,7 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
         }
     }
     CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
-    CUDA_TRY(cudaMemcpyAsync(p->h_state, p->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
@@ -411,7 +541,8 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     }
     p->last_gemm_flops = gemm_flops;
     p->last_gemm_launches = (int64_t)n_gemm;
-    *result = p->h_state->acc;
+    *result = p->h_readback->acc;
+    p->runs++;
     return TOB_OK;
 }
 

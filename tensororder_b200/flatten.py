@@ -47,7 +47,43 @@ def _host_factory(shape, default_value=None):
     return np.full(shape, default_value, dtype=np.float64)
 
 
-def flatten_plan(plan, tensor_factory=_host_factory) -> FlatPlan:
+class _LeafArena:
+    """`tensor_factory` that hands out views of one growing float64 buffer, so the reference's
+    `Tensor.build(factory)` writes each leaf straight into the buffer passed to `tob_plan_upload`
+    (no per-leaf allocation, no concatenate)."""
+
+    def __init__(self, capacity=4096):
+        self.buf = np.empty(capacity, dtype=np.float64)
+        self.used = 0
+
+    def factory(self, shape, default_value=None):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        if self.used + n > self.buf.shape[0]:
+            grown = np.empty(max(2 * self.buf.shape[0], self.used + n), dtype=np.float64)
+            grown[: self.used] = self.buf[: self.used]
+            self.buf = grown
+        view = self.buf[self.used: self.used + n].reshape(shape)
+        if default_value is not None:
+            view[...] = default_value
+        return view
+
+    def commit(self, built, n):
+        """Keep `built` (normally the view just handed out) as the next n doubles of the buffer."""
+        offset = self.used
+        target = self.buf[offset: offset + n]
+        if not (isinstance(built, np.ndarray) and built.dtype == np.float64 and np.shares_memory(built, target)
+                and built.flags["C_CONTIGUOUS"]):
+            if offset + n > self.buf.shape[0]:
+                self.factory((n,))  # grow
+                target = self.buf[offset: offset + n]
+            target[:] = np.asarray(built, dtype=np.float64).reshape(-1)
+        self.used = offset + n
+        return offset
+
+
+def flatten_plan(plan, tensor_factory=None) -> FlatPlan:
     network = plan.network
     # edge id -> slice group index (non-empty groups only, in order)
     group_of = {}
@@ -67,7 +103,8 @@ def flatten_plan(plan, tensor_factory=_host_factory) -> FlatPlan:
     axis_start: List[int] = [0]
     axis_edge: List[int] = []
     leaf_tensor_index: List[int] = []
-    chunks: List[np.ndarray] = []
+    arena = _LeafArena()
+    chunks: List[np.ndarray] = []  # only with a caller-supplied factory
     built_at = {}  # tensor index -> offset (a tensor named by two leaves is stored once)
     total = 0
     stack: List[int] = []
@@ -76,22 +113,31 @@ def flatten_plan(plan, tensor_factory=_host_factory) -> FlatPlan:
         if node.is_leaf:
             t = int(node.tensor_index)
             edges = [int(e) for e in network.index_list(t)]
-            for e in edges:
-                if e < 0:
-                    raise ValueError("tensor %d has a dangling index; the network cannot contract to a scalar" % t)
+            if edges and min(edges) < 0:
+                raise ValueError("tensor %d has a dangling index; the network cannot contract to a scalar" % t)
             if t not in built_at:
-                data = np.ascontiguousarray(network[t].build(tensor_factory), dtype=np.float64)
-                if data.size != 2 ** len(edges):
-                    raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
-                built_at[t] = total
-                chunks.append(data.reshape(-1))
-                total += data.size
+                size = 1 << len(edges)
+                if tensor_factory is None:
+                    built = network[t].build(arena.factory)
+                    if getattr(built, "size", size) != size:
+                        raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
+                    built_at[t] = arena.commit(built, size)
+                else:
+                    data = np.ascontiguousarray(network[t].build(tensor_factory), dtype=np.float64)
+                    if data.size != size:
+                        raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
+                    built_at[t] = total
+                    chunks.append(data.reshape(-1))
+                    total += data.size
             node_left.append(-1)
             node_right.append(-1)
             node_leaf.append(len(leaf_rank))
             leaf_rank.append(len(edges))
             leaf_off.append(built_at[t])
-            axis_edge.extend(-(group_of[e] + 1) if e in group_of else e for e in edges)
+            if group_of:
+                axis_edge.extend(-(group_of[e] + 1) if e in group_of else e for e in edges)
+            else:
+                axis_edge.extend(edges)
             axis_start.append(len(axis_edge))
             leaf_tensor_index.append(t)
         else:
@@ -103,7 +149,10 @@ def flatten_plan(plan, tensor_factory=_host_factory) -> FlatPlan:
         stack.append(pos)
     if len(stack) != 1:
         raise ValueError("contraction tree is not a single rooted tree")
-    leaf_data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.float64)
+    if tensor_factory is None:
+        leaf_data = arena.buf[: arena.used]
+    else:
+        leaf_data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.float64)
     return FlatPlan(
         node_left=np.asarray(node_left, dtype=np.int32),
         node_right=np.asarray(node_right, dtype=np.int32),

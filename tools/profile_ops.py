@@ -26,7 +26,10 @@ print("%s%s: %d ops, one slice %.3f ms, count(slice 0) %r, peak %.2f GB" % (name
 rows = sorted(zip(ms, ops), key=lambda x: -x[0])[:top]
 out = []
 for t, op in rows:
-    if op["kind"] == 2:
+    if op["kind"] in (2, 3):
+        if op["kind"] == 3:
+            print("  microtree launch: %d joins in %d CTAs  %9.4f ms  %5.1f%% of slice" % (
+                len(op["micro"]), len(op["cta_start"]) - 1, t, 100 * t / tot))
         continue
     tf = op["flops"] / (t * 1e-3) / 1e12
     gb = op["bytes"] / (t * 1e-3) / 1e9
@@ -39,7 +42,7 @@ for t, op in rows:
                 "tflops": tf, "gbs": gb, "bound": bound, "frac": frac})
 by_kind = {}
 for t, op in zip(ms, ops):
-    key = {0: "generic", 1: "gemm", 2: "accum"}[op["kind"]]
+    key = {0: "generic", 1: "gemm", 2: "accum", 3: "microtree"}[op["kind"]]
     by_kind.setdefault(key, [0, 0.0])
     by_kind[key][0] += 1
     by_kind[key][1] += t
