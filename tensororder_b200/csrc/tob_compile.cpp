@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <set>
@@ -30,6 +31,15 @@ static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // Kernel choice for a canonical join  C[2^(m+n)] = A[2^m x 2^k] . B[2^n x 2^k]^T
 // ------------------------------------------------------------------------------------------------
+int gemm_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TOB_GEMM_VARIANT");
+        v = e ? atoi(e) : 3;
+    }
+    return v;
+}
+
 void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     const int m = op->m, n = op->n, k = op->k;
     op->flops = 2.0 * std::ldexp(1.0, m + n + k);
@@ -40,6 +50,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
         op->kind = OP_GEMM;
         op->tm_log2 = std::min(m, 7);
         op->tn_log2 = std::min(n, 7);
+        if (gemm_variant() == 3 && op->tn_log2 == 7) op->tn_log2 = 6;
         int64_t tiles = (int64_t)1 << ((m - op->tm_log2) + (n - op->tn_log2));
         int ks = 0;
         if (allow_splitk && tiles < 8 * kNumSMs) {

@@ -100,4 +100,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk);
 
 void set_error(const std::string& msg);
 
+// Experiment switch for the 128x128 DMMA GEMM (see tob_kernels.cu); 3 = prefer 128x64 tiles, 2 CTAs per SM.
+int gemm_variant();
+
 }  // namespace tob

@@ -197,21 +197,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // K step per pipeline stage (doubles) and the padded shared-memory row stride: stride == 4 (mod 16)
 // makes the 8x4 DMMA fragment loads (LDS.64) conflict-free for both TK = 16 and TK = 32.
-template <int TK>
-struct GemmCfg {
-    static constexpr int LDS = TK + 4;
-    static constexpr int CHUNKS = TK / 2;        // 16-byte chunks per tile row
-    static constexpr int ROWS_PER_PASS = 256 / CHUNKS;
-};
-
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES>
-__global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NT = WM * WN * 32;             // threads per CTA
     constexpr int WTM = TM / WM, WTN = TN / WN;  // warp tile
     constexpr int MB = WTM / 8, NB = WTN / 8;    // 8x8 DMMA blocks per warp tile
-    constexpr int LDS = GemmCfg<TK>::LDS, CHUNKS = GemmCfg<TK>::CHUNKS, RPP = GemmCfg<TK>::ROWS_PER_PASS;
+    constexpr int LDS = TK + 4;                  // row stride == 4 (mod 16): conflict-free LDS.64 fragments
+    constexpr int CHUNKS = TK / 2;               // 16-byte chunks per tile row
+    constexpr int RPP = NT / CHUNKS;             // rows per loader pass
     constexpr int K4 = TK / 4;
-    static_assert(WM * WN == 8, "8 warps");
     static_assert(TM % RPP == 0 && TN % RPP == 0, "loader passes");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
@@ -224,8 +219,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_dmma(KParams p) {
     const int wm = warp % WM, wn = warp / WM;
     const int k = p.k, ks = p.ksplit_log2;
 
-    for (int i = tid; i < TM; i += 256) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
-    for (int i = tid; i < TN; i += 256) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+    for (int i = tid; i < TM; i += NT) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NT) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
 
     // ---- work decode: 1-D grid over (split, tile), tiles rasterised in groups of 16 M-tiles ----
     const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
@@ -326,20 +321,13 @@ constexpr size_t gemm_smem_bytes() {
     return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (TK + 4) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
 }
 
-// variant table: [0] = 128x128 TK16x4 stages, [1] = 128x128 TK32x3 stages (fewer CTA barriers per flop)
-#define GEMM_77_A k_gemm_dmma<7, 7, 2, 4, 16, 4>
-#define GEMM_77_B k_gemm_dmma<7, 7, 2, 4, 32, 3>
-#define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 4>
-#define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4>
-
-static int g_gemm_variant = -1;
-static int gemm_variant() {
-    if (g_gemm_variant < 0) {
-        const char* e = getenv("TOB_GEMM_VARIANT");
-        g_gemm_variant = e ? atoi(e) : 1;
-    }
-    return g_gemm_variant;
-}
+// 128x128 variants (TOB_GEMM_VARIANT): 0 = 8 warps TK16 x4 stages; 1 = 8 warps TK32 x3 stages (default: fewer
+// CTA barriers per flop); 2 = 16 warps (32x32 warp tiles) TK32 x3 stages.  128x64 runs 2 CTAs per SM.
+#define GEMM_77_A k_gemm_dmma<7, 7, 2, 4, 16, 4, 1>
+#define GEMM_77_B k_gemm_dmma<7, 7, 2, 4, 32, 3, 1>
+#define GEMM_77_C k_gemm_dmma<7, 7, 4, 4, 32, 3, 1>
+#define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
+#define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -347,7 +335,9 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_77_B, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 32, 3>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 4>());
+    e = cudaFuncSetAttribute(GEMM_77_C, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 32, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     return e;
@@ -456,13 +446,16 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         const unsigned long long blocks = tiles << op.ksplit_log2;
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
         if (op.tm_log2 == 7 && op.tn_log2 == 7) {
-            // the TK=32 variant needs K per split >= 32
-            if (gemm_variant() == 1 && (op.k - op.ksplit_log2) >= 5)
+            const int v = gemm_variant();
+            const bool k32 = (op.k - op.ksplit_log2) >= 5;  // the TK=32 variants need >= 32 K elements per split
+            if (v == 2 && k32)
+                GEMM_77_C<<<(unsigned)blocks, 512, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
+            else if (v >= 1 && k32)
                 GEMM_77_B<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
             else
                 GEMM_77_A<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 16, 4>(), stream>>>(p);
         } else if (op.tm_log2 == 7 && op.tn_log2 == 6)
-            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 4>(), stream>>>(p);
+            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
         else if (op.tm_log2 == 6 && op.tn_log2 == 6)
             GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
         else
