@@ -292,6 +292,8 @@ def b200_arm(args, rank, world, local_rank):
     h2d = d2h = 0
     e2e_total = 0.0
     e2e_counts = None
+    e2e_parts = {"flatten_compile_s": 0.0, "upload_s": 0.0, "run_s": 0.0, "device_ms": 0.0}
+    e2e_step_s = []
     for step in range(1 + e2e_steps):  # one warm-up pass
         barrier()
         t0 = time.perf_counter()
@@ -309,6 +311,9 @@ def b200_arm(args, rank, world, local_rank):
             host[j] = got / world if it["owner"] is None else got
             h2d += api.last_stats["h2d_bytes"]
             d2h += api.last_stats["d2h_bytes"]
+            if step >= 1:
+                for key in e2e_parts:
+                    e2e_parts[key] += api.last_stats[key]
         vec = torch.from_numpy(host).to(dev)
         reduce_counts(vec)
         e2e_counts = vec.cpu().numpy()
@@ -318,6 +323,7 @@ def b200_arm(args, rank, world, local_rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if step >= 1:
             e2e_total += float(dt.item())
+            e2e_step_s.append(float(dt.item()))
     bytes_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
@@ -342,7 +348,9 @@ def b200_arm(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
-                    "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
+                    "step_seconds": e2e_step_s,
+                    "rank0_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(lt.item()), "clocks": clocks, "counts_ok": ok, "instances": n_inst,
         }
         if gemm_launches > 0:

@@ -2,6 +2,7 @@
 // as a CUDA graph, per-op profiling, stand-alone tensordot / permute.
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -77,6 +78,8 @@ std::vector<StreamSet> g_free_streams;
 const size_t kMaxCachedBlock = (size_t)2 << 30;
 const size_t kMaxCachedTotal = (size_t)8 << 30;
 
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 void pool_trim_locked(int device, size_t keep_bytes) {
     size_t total = 0;
     for (const Block& b : g_free_blocks)
@@ -101,13 +104,28 @@ cudaError_t pool_acquire(size_t bytes, int device, bool pinned, Block* out) {
         for (size_t i = 0; i < g_free_blocks.size(); i++) {
             const Block& b = g_free_blocks[i];
             if (b.pinned != pinned || (!pinned && b.device != device) || b.size < bytes) continue;
-            if (b.size > 4 * bytes + ((size_t)64 << 20)) continue;  // do not burn a huge block on a tiny plan
             if (best < 0 || b.size < g_free_blocks[best].size) best = (int)i;
         }
         if (best >= 0) {
             *out = g_free_blocks[best];
             g_free_blocks.erase(g_free_blocks.begin() + best);
             return cudaSuccess;
+        }
+    }
+    // nothing cached fits: allocate with headroom (so a slightly larger plan later still fits) and drop
+    // the largest cached block that was too small, keeping the pool from growing without bound
+    if (bytes < kMaxCachedBlock / 2) bytes = align_up(bytes + bytes / 4, 4096);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int big = -1;
+        for (size_t i = 0; i < g_free_blocks.size(); i++) {
+            const Block& b = g_free_blocks[i];
+            if (b.pinned != pinned || (!pinned && b.device != device)) continue;
+            if (big < 0 || b.size > g_free_blocks[big].size) big = (int)i;
+        }
+        if (big >= 0) {
+            if (pinned) cudaFreeHost(g_free_blocks[big].ptr); else cudaFree(g_free_blocks[big].ptr);
+            g_free_blocks.erase(g_free_blocks.begin() + big);
         }
     }
     void* ptr = nullptr;
@@ -161,7 +179,6 @@ void streams_release(const StreamSet& s) {
     g_free_streams.push_back(s);
 }
 
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
 static int ensure_device(int device) {
@@ -270,8 +287,14 @@ void tob_plan_destroy(tob_plan* p) {
     delete p;
 }
 
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     if (!p || !leaf_data) { set_error("NULL argument"); return TOB_E_INVALID; }
+    static const bool trace = getenv("TOB_TRACE") != nullptr;
+    const double t_begin = now_ms();
     Program& G = p->prog;
     if (n_doubles != G.src_leaf_len) { set_error("leaf buffer length does not match the plan"); return TOB_E_INVALID; }
     int rc = ensure_device(p->device);
@@ -283,12 +306,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         set_error("plan needs " + std::to_string(need) + " bytes, above mem_limit_bytes");
         return TOB_E_OOM;
     }
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    if ((size_t)need > free_b) {
-        set_error("plan needs " + std::to_string(need) + " bytes, device has " + std::to_string(free_b) + " free");
-        return TOB_E_OOM;
-    }
+    const double t_dev = now_ms();
     StreamSet ss;
     CUDA_TRY(streams_acquire(p->device, &ss));
     p->own_stream = ss.stream;
@@ -331,8 +349,21 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     const size_t o_ws = section((size_t)G.ws_doubles * 8);
     const size_t total_bytes = off + 256;
 
+    const double t_tables = now_ms();
     Block db, hb;
-    CUDA_TRY(pool_acquire(total_bytes, p->device, false, &db));
+    {
+        cudaError_t e = pool_acquire(total_bytes, p->device, false, &db);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            set_error("plan needs " + std::to_string(total_bytes) + " bytes, device has " + std::to_string(free_b) + " free");
+            streams_release(ss);
+            p->own_stream = nullptr; p->stream = nullptr; p->ev0 = p->ev1 = nullptr;
+            return TOB_E_OOM;
+        }
+        CUDA_TRY(e);
+    }
     p->d_block = db.ptr;
     p->d_block_size = db.size;
     CUDA_TRY(pool_acquire(prefix_bytes + 256, p->device, true, &hb));
@@ -355,6 +386,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     p->h_state = reinterpret_cast<DevState*>(h + o_state);
     p->h_readback = reinterpret_cast<DevState*>(h + prefix_bytes);
 
+    const double t_alloc = now_ms();
     // ---- fill the pinned mirror: tables, micro programs, leaves permuted into canonical order ----
     memset(h, 0, o_leaves);
     memcpy(h + o_term, term_start.data(), sizeof(int32_t) * (L + 1));
@@ -390,9 +422,13 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         }
         for (int64_t e = n; e < (int64_t)align_up((size_t)n, 32); e++) dst[e] = 0.0;
     }
+    const double t_fill = now_ms();
     // ---- ONE pinned host->device copy: state, tables, micro programs, leaves ----
     CUDA_TRY(cudaMemcpyAsync(p->d_block, p->h_block, prefix_bytes, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (trace)
+        fprintf(stderr, "[tob] upload: ensure_device %.3f  streams+tables %.3f  alloc %.3f  fill %.3f  h2d+sync %.3f ms (%zu B)\n",
+                t_dev - t_begin, t_tables - t_dev, t_alloc - t_tables, t_fill - t_alloc, now_ms() - t_fill, prefix_bytes);
     p->uploaded = true;
     return TOB_OK;
 }
