@@ -95,6 +95,73 @@ __global__ void __launch_bounds__(256) k_generic_t1(KParams p) {
     }
 }
 
+// Streaming form of k_generic_t1 for large outputs: one thread produces FOUR consecutive outputs (one
+// 32-byte store), so the two pext's are paid once per four outputs and the A / B rows of neighbouring
+// outputs are fetched with 16-byte loads.  KL = log2 K (compile time, 0..3) or -1 for a run-time K <= 64;
+// LOW = mask_m & 3 says which of the two lowest C address bits belong to the M side.
+template <int KL, int LOW>
+__global__ void __launch_bounds__(256) k_generic_t1x4(KParams p) {
+    const double* A = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* B = operand_base(p.b, p.leaf_off, p.b_leaf);
+    const unsigned long long quads = 1ull << (p.m + p.n - 2);
+    const int k = (KL >= 0) ? KL : p.k;
+    for (unsigned long long q = blockIdx.x * 256ull + threadIdx.x; q < quads; q += (unsigned long long)gridDim.x * 256ull) {
+        const unsigned long long c0 = q << 2;
+        const unsigned long long mi0 = pext_runs(c0, p.runs_m);
+        const unsigned long long ni0 = pext_runs(c0, p.runs_n);
+        double out[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int dm = (LOW == 3) ? j : (LOW == 1) ? (j & 1) : (LOW == 2) ? (j >> 1) : 0;
+            const int dn = (LOW == 0) ? j : (LOW == 1) ? (j >> 1) : (LOW == 2) ? (j & 1) : 0;
+            const double* ar = A + ((mi0 + dm) << k);
+            const double* br = B + ((ni0 + dn) << k);
+            double s;
+            if (KL == 0) {
+                s = ar[0] * br[0];
+            } else if (KL > 0) {
+                const double2* a2 = reinterpret_cast<const double2*>(ar);
+                const double2* b2 = reinterpret_cast<const double2*>(br);
+                s = 0.0;
+#pragma unroll
+                for (int i = 0; i < (1 << (KL > 0 ? KL - 1 : 0)); i++) {
+                    const double2 x = a2[i], y = b2[i];
+                    s = fma(x.x, y.x, s);
+                    s = fma(x.y, y.y, s);
+                }
+            } else {
+                if (k == 0) {
+                    s = ar[0] * br[0];
+                } else {
+                    const double2* a2 = reinterpret_cast<const double2*>(ar);
+                    const double2* b2 = reinterpret_cast<const double2*>(br);
+                    const int K2 = 1 << (k > 0 ? k - 1 : 0);
+                    s = 0.0;
+                    for (int i = 0; i < K2; i++) {
+                        const double2 x = a2[i], y = b2[i];
+                        s = fma(x.x, y.x, s);
+                        s = fma(x.y, y.y, s);
+                    }
+                }
+            }
+            out[j] = s;
+        }
+        double2* dst = reinterpret_cast<double2*>(p.c + c0);
+        dst[0] = make_double2(out[0], out[1]);
+        dst[1] = make_double2(out[2], out[3]);
+    }
+}
+
+template <int KL>
+static void launch_t1x4(const KParams& p, unsigned grid, cudaStream_t stream) {
+    switch ((int)(p.mask_m & 3ull)) {
+        case 0: k_generic_t1x4<KL, 0><<<grid, 256, 0, stream>>>(p); break;
+        case 1: k_generic_t1x4<KL, 1><<<grid, 256, 0, stream>>>(p); break;
+        case 2: k_generic_t1x4<KL, 2><<<grid, 256, 0, stream>>>(p); break;
+        default: k_generic_t1x4<KL, 3><<<grid, 256, 0, stream>>>(p); break;
+    }
+}
+
 // one warp per output element; 128 <= K
 __global__ void __launch_bounds__(256) k_generic_t32(KParams p) {
     const double* A = operand_base(p.a, p.leaf_off, p.a_leaf);
@@ -460,6 +527,17 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
         else
             return cudaErrorInvalidConfiguration;
+        (*launches)++;
+    } else if (op.threads_per_out == 1 && op.m + op.n >= 12) {
+        // large outputs: 4 outputs per thread, 32-byte stores
+        const unsigned grid = grid_for(outs >> 2, 256, cap);
+        switch (op.k) {
+            case 0: launch_t1x4<0>(p, grid, stream); break;
+            case 1: launch_t1x4<1>(p, grid, stream); break;
+            case 2: launch_t1x4<2>(p, grid, stream); break;
+            case 3: launch_t1x4<3>(p, grid, stream); break;
+            default: launch_t1x4<-1>(p, grid, stream); break;
+        }
         (*launches)++;
     } else if (op.threads_per_out == 1) {
         k_generic_t1<<<grid_for(outs, 256, cap), 256, 0, stream>>>(p);
