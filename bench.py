@@ -252,6 +252,8 @@ def b200_arm(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         host = np.zeros(n_inst)
+        if timed:
+            torch.cuda.nvtx.range_push("timed_step")  # ncu --nvtx --nvtx-include "timed_step/" selects these launches
         with torch.cuda.stream(stream):
             e0.record(stream)
             for j, it in enumerate(items):
@@ -271,6 +273,8 @@ def b200_arm(args, rank, world, local_rank):
             reduce_counts(counts)
             e1.record(stream)
         stream.synchronize()
+        if timed:
+            torch.cuda.nvtx.range_pop()
         barrier()
         if timed:
             step_ms.append(e0.elapsed_time(e1))

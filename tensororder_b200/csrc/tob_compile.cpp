@@ -191,6 +191,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             NodeInfo& B = P->nodes[X.right];
             A.parent = i;
             B.parent = i;
+            X.edges.reserve(A.edges.size() + B.edges.size());
             std::set_symmetric_difference(A.edges.begin(), A.edges.end(), B.edges.begin(), B.edges.end(),
                                           std::back_inserter(X.edges));
             X.slice_dependent = A.slice_dependent || B.slice_dependent;
@@ -203,18 +204,27 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         return fail("root tensor is not rank 0 (the network has open indices)");
 
     // ---- canonical layouts (top-down) ----
+    int32_t max_edge = -1;
+    for (const NodeInfo& X : P->nodes)
+        for (int32_t e : X.edges) max_edge = std::max(max_edge, e);
+    std::vector<int32_t> stamp((size_t)max_edge + 2, -1);  // stamp[e] == tag  <=>  e in the tagged node's edge set
     for (int i = N - 1; i >= 0; i--) {
         NodeInfo& X = P->nodes[i];
         if (X.leaf >= 0) continue;
         NodeInfo& A = P->nodes[X.left];
         NodeInfo& B = P->nodes[X.right];
         std::vector<int32_t> K;
+        K.reserve(std::min(A.edges.size(), B.edges.size()));
         std::set_intersection(A.edges.begin(), A.edges.end(), B.edges.begin(), B.edges.end(), std::back_inserter(K));
-        for (NodeInfo* C : {&A, &B}) {
+        for (int side = 0; side < 2; side++) {
+            NodeInfo* C = side ? &B : &A;
+            const int32_t tag = side ? X.right : X.left;
+            for (int32_t e : C->edges) stamp[e] = tag;
+            C->layout.reserve(C->edges.size());
             C->layout = K;  // ascending edge id, identical for both siblings
             C->k_with_sibling = (int)K.size();
             for (int32_t e : X.layout)
-                if (contains(C->edges, e)) C->layout.push_back(e);
+                if (stamp[e] == tag) C->layout.push_back(e);
             if (C->layout.size() != C->edges.size()) return fail("internal: layout does not cover the node's edges");
         }
     }
@@ -270,8 +280,9 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         op.a = A.where;
         op.b = B.where;
         uint64_t mask = 0;
+        for (int32_t e : A.edges) stamp[e] = -2 - i;  // unique tag per join
         for (size_t p = 0; p < X.layout.size(); p++)
-            if (contains(A.edges, X.layout[p])) mask |= (uint64_t)1 << p;
+            if (stamp[X.layout[p]] == -2 - i) mask |= (uint64_t)1 << p;
         op.mask_m = mask;
         if (op.n > op.m) {  // keep the larger free side as M (the GEMM tiles assume m >= n)
             std::swap(op.a, op.b);

@@ -55,6 +55,7 @@ class _LeafArena:
     def __init__(self, capacity=4096):
         self.buf = np.empty(capacity, dtype=np.float64)
         self.used = 0
+        self._last = None
 
     def factory(self, shape, default_value=None):
         n = 1
@@ -67,11 +68,15 @@ class _LeafArena:
         view = self.buf[self.used: self.used + n].reshape(shape)
         if default_value is not None:
             view[...] = default_value
+        self._last = view
         return view
 
     def commit(self, built, n):
         """Keep `built` (normally the view just handed out) as the next n doubles of the buffer."""
         offset = self.used
+        if built is self._last:  # the usual case: build() filled and returned the view it was handed
+            self.used = offset + n
+            return offset
         target = self.buf[offset: offset + n]
         if not (isinstance(built, np.ndarray) and built.dtype == np.float64 and np.shares_memory(built, target)
                 and built.flags["C_CONTIGUOUS"]):
