@@ -45,7 +45,10 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     op->flops = 2.0 * std::ldexp(1.0, m + n + k);
     op->bytes = 8.0 * (std::ldexp(1.0, m + k) + std::ldexp(1.0, n + k) + std::ldexp(1.0, m + n));
     op->ksplit_log2 = 0;
-    const bool gemm_ok = (k >= 4 && m >= 6 && n >= 6 && (m + n + k) >= 20);
+    // k >= 4: the DMMA pipeline proper.  1 <= k <= 3 with a large two-sided output (outer-product-like
+    // joins): the same kernel with a zero-filled K step, i.e. a tiled store kernel with full operand
+    // reuse, instead of one thread per output re-reading both rows from L2.
+    const bool gemm_ok = (k >= 4 && m >= 6 && n >= 6 && (m + n + k) >= 20) || (k >= 1 && k <= 3 && m >= 7 && n >= 7 && (m + n) >= 18);
     if (kernel_policy != 1 && gemm_ok) {
         op->kind = OP_GEMM;
         op->tm_log2 = std::min(m, 7);

@@ -252,6 +252,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 }
+// 16-byte cp.async whose source contributes only src_bytes (0 or 16); the rest of the chunk is zero-filled
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -300,7 +305,8 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     const unsigned long long tile_m = gidx * group + (r % group), tile_n = r / group;
 
     const unsigned long long Ksplit = (1ull << k) >> ks;
-    const int KT = (int)(Ksplit / TK);
+    const int KT = (int)((Ksplit + TK - 1) / TK);
+    const bool partial = Ksplit < (unsigned long long)TK;  // K = 2, 4, 8 (< one K step): zero-fill the tail chunks
     const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
     const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
 
@@ -314,6 +320,15 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
         double* bs = Bs + s * TN * LDS + dst_off;
         const double* ag = a_src + kt * TK;
         const double* bg = b_src + kt * TK;
+        if (partial) {
+            const int nbytes = ((unsigned long long)(chunk * 2) < Ksplit) ? 16 : 0;
+            const int back = nbytes ? 0 : chunk * 2;  // keep the (unused) source address inside the row
+#pragma unroll
+            for (int i = 0; i < TM / RPP; i++) cp_async16_zfill(as + i * RPP * LDS, ag + i * pass_stride - back, nbytes);
+#pragma unroll
+            for (int i = 0; i < TN / RPP; i++) cp_async16_zfill(bs + i * RPP * LDS, bg + i * pass_stride - back, nbytes);
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < TM / RPP; i++) cp_async16(as + i * RPP * LDS, ag + i * pass_stride);
 #pragma unroll

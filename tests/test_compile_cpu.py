@@ -94,7 +94,7 @@ def test_forced_generic_policy_and_gemm_selection():
     assert 1 in kinds, "the dominant joins of n=150 must go to the DMMA GEMM kernel"
     for op in auto["slice_ops"]:
         if op["kind"] == 1:
-            assert op["m"] >= op["n"] >= 6 and op["k"] >= 4
+            assert op["m"] >= op["n"] >= 6 and (op["k"] >= 4 or (op["k"] >= 1 and op["m"] + op["n"] >= 18))
             assert op["k"] - op["ksplit_log2"] >= 7 or op["ksplit_log2"] == 0
     forced = CompiledPlan(flat, kernel_policy=1).describe()
     assert all(op["kind"] in (0, 2, 3) for op in forced["slice_ops"])

@@ -37,6 +37,7 @@ CASES = [
     (0, 0, 0), (3, 0, 0), (0, 4, 0), (3, 2, 0), (5, 5, 5), (10, 3, 1), (12, 2, 2), (3, 12, 2),
     (9, 9, 5), (14, 14, 14), (20, 20, 20), (16, 10, 8), (15, 13, 7), (13, 14, 6), (14, 12, 4),
     (18, 16, 9), (17, 17, 10), (20, 12, 6), (21, 18, 9), (13, 13, 1), (12, 12, 0), (22, 8, 8),
+    (12, 11, 2), (11, 13, 3), (14, 10, 3), (16, 3, 1), (17, 2, 0),  # small-k GEMM (zero-filled K step) and x4 streaming kernel
 ]
 
 
