@@ -101,6 +101,14 @@ int tob_plan_upload(tob_plan* plan, const double* leaf_data, int64_t n_doubles);
  * first=rank, stride=world gives the per-GPU partial sum of the multi-GPU partition. */
 int tob_plan_run(tob_plan* plan, uint64_t first, uint64_t count, uint64_t stride, double* result);
 
+/* Continuation form: the device accumulator starts at `initial` (so chunked calls reproduce the
+ * sequential slice-order sum bit for bit) and TOB_RUN_SKIP_INVARIANT skips the slice-invariant
+ * prologue already computed by an earlier call on this plan.  Lets the Python host return to the
+ * interpreter between chunks of slices, where the reference's SIGALRM timeout (util.py:32-39) fires. */
+#define TOB_RUN_SKIP_INVARIANT 1
+int tob_plan_run_ex(tob_plan* plan, uint64_t first, uint64_t count, uint64_t stride, double initial,
+                    int32_t flags, double* result);
+
 /* Device time (CUDA events on the plan's stream) of the last tob_plan_run, in milliseconds. */
 double tob_plan_last_ms(const tob_plan* plan);
 

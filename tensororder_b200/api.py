@@ -102,16 +102,43 @@ class CompiledPlan:
             raise RuntimeError("tob_plan_upload: " + cabi.last_error())
         self.uploaded = True
 
-    def run(self, first: int = 0, count: Optional[int] = None, stride: int = 1) -> float:
+    def run(self, first: int = 0, count: Optional[int] = None, stride: int = 1, initial: float = 0.0,
+            skip_invariant: bool = False) -> float:
         if count is None:
             count = (self.num_slices - first + stride - 1) // stride
         out = c_double(0.0)
-        rc = cabi.lib.tob_plan_run(self._handle, first, count, stride, byref(out))
+        rc = cabi.lib.tob_plan_run_ex(self._handle, first, count, stride, float(initial), 1 if skip_invariant else 0,
+                                      byref(out))
         if rc == cabi.TOB_E_OOM:
             raise _oom_class()(cabi.last_error())
         if rc != cabi.TOB_OK:
             raise RuntimeError("tob_plan_run: " + cabi.last_error())
         return out.value
+
+    def run_interruptible(self, first: int = 0, count: Optional[int] = None, stride: int = 1, target_s: float = 0.25):
+        """Same result as `run` (bit for bit: the device accumulator is carried across calls), but
+        returns to the interpreter every ~target_s seconds of device work so pending signal handlers —
+        the reference's SIGALRM `TimeoutTimer` (src/util/util.py:32-39) — run between chunks of slices."""
+        if count is None:
+            count = (self.num_slices - first + stride - 1) // stride
+        acc, done, chunk = 0.0, 0, 1
+        total_ms, launches = 0.0, 0
+        gemm = [0.0, 0.0, 0]
+        while done < count or (count == 0 and done == 0):
+            c = min(chunk, count - done)
+            acc = self.run(first + done * stride, c, stride, initial=acc, skip_invariant=done > 0)
+            ms = self.last_ms
+            total_ms += ms
+            launches += self.last_launches
+            g = self.last_gemm
+            gemm = [gemm[0] + g[0], gemm[1] + g[1], gemm[2] + g[2]]
+            done += max(c, 1)
+            if c > 0 and ms > 0:
+                chunk = max(1, min(count, int(c * target_s * 1e3 / ms)))
+            if count == 0:
+                break
+        self.interruptible_stats = {"device_ms": total_ms, "launches": launches, "gemm": tuple(gemm)}
+        return acc
 
     @property
     def last_ms(self) -> float:
@@ -221,12 +248,13 @@ class B200API:
             if num_slice_limit is not None:
                 total = min(total, int(num_slice_limit))  # itertools.islice(slices, N), base_api.py:23-24
             count = 0 if rank >= total else (total - rank + world - 1) // world
-            partial = compiled.run(first=rank if count else 0, count=count, stride=world)
+            partial = compiled.run_interruptible(first=rank if count else 0, count=count, stride=world)
             t3 = time.perf_counter()
             result = self._all_reduce(partial) if world > 1 else partial
             self.last_stats = {
                 "flatten_compile_s": t1 - t0, "upload_s": t2 - t1, "run_s": t3 - t2,
-                "device_ms": compiled.last_ms, "launches": compiled.last_launches,
+                "device_ms": compiled.interruptible_stats["device_ms"],
+                "launches": compiled.interruptible_stats["launches"],
                 "h2d_bytes": int(flat.leaf_data.nbytes), "d2h_bytes": 32,
                 "peak_bytes": compiled.peak_bytes, "slices": total, "rank": rank, "world": world,
             }

@@ -488,6 +488,11 @@ static cudaError_t launch_slice(tob_plan* p, int* launches) {
 }
 
 int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double* result) {
+    return tob_plan_run_ex(p, first, count, stride, 0.0, 0, result);
+}
+
+int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double initial, int32_t flags,
+                    double* result) {
     if (!p || !result) { set_error("NULL argument"); return TOB_E_INVALID; }
     if (!p->uploaded) { set_error("tob_plan_upload has not been called"); return TOB_E_INVALID; }
     const uint64_t nslices = tob_plan_num_slices(p);
@@ -500,10 +505,11 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     int launches = 0;
     p->h_state->next_slice = first;
     p->h_state->stride = stride;
-    p->h_state->acc = 0.0;
+    p->h_state->acc = initial;
     p->h_state->pad = 0.0;
     CUDA_TRY(cudaMemcpyAsync(p->d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
+    const bool skip_invariant = (flags & TOB_RUN_SKIP_INVARIANT) != 0 && p->runs > 0;
     const int ug = p->prog.opt.use_graph;
     // auto: launch-bound slices replay as a graph, but only once the plan is being reused (second run or
     // several slices): a plan that runs a single slice once never pays capture + instantiate
@@ -531,10 +537,11 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
         return TOB_OK;
     };
     if (count > 0) {
-        for (const Op& op : p->prog.invariant_ops) {
-            int rc2 = timed_op(op);
-            if (rc2 != TOB_OK) return rc2;
-        }
+        if (!skip_invariant)
+            for (const Op& op : p->prog.invariant_ops) {
+                int rc2 = timed_op(op);
+                if (rc2 != TOB_OK) return rc2;
+            }
         if (as_graph) {
             if (!p->graph_exec) {
                 int per_slice = 0;

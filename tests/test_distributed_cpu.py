@@ -30,9 +30,11 @@ def _worker(rank, world, port, name, variant, limit, out):
     def fake_upload(self):
         self.uploaded = True
 
-    def fake_run(self, first=0, count=None, stride=1):
-        calls["args"] = (first, count, stride)
-        return run_program(self.describe(), self.flat, first=first, count=count, stride=stride) if count else 0.0
+    def fake_run(self, first=0, count=None, stride=1, initial=0.0, skip_invariant=False):
+        # the interruptible loop issues chunks; record the whole range this rank was given
+        a = calls.setdefault("args", [first, 0, stride])
+        a[1] += count
+        return initial + (run_program(self.describe(), self.flat, first=first, count=count, stride=stride) if count else 0.0)
 
     api_mod.CompiledPlan.upload = fake_upload
     api_mod.CompiledPlan.run = fake_run
@@ -42,7 +44,7 @@ def _worker(rank, world, port, name, variant, limit, out):
     api = api_mod.B200API()
     api.add_argument("entry_type", "float64")
     got = api.contract_sliced(pp.as_execution_plan(), num_slice_limit=limit)
-    out[rank] = (float(got), calls["args"], api.last_stats["world"])
+    out[rank] = (float(got), tuple(calls["args"]), api.last_stats["world"])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -124,6 +124,42 @@ def test_microtree_kernel_matches_per_join_launches(name):
     assert on.last_stats["launches"] < off.last_stats["launches"]
 
 
+def test_interruptible_run_is_bit_identical_and_honours_sigalrm():
+    """The slice loop returns to the interpreter between chunks (the reference's TimeoutTimer is a SIGALRM
+    handler raising TimeoutError, src/util/util.py:32-39) and carries the device accumulator across
+    chunks, so the result equals the single-call sequential sum bit for bit."""
+    import signal
+    import time
+
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden("vc150_lineflow").variant("min4")
+    cp = CompiledPlan(flatten_plan(pp.as_execution_plan()))
+    cp.upload()
+    one = cp.run()
+    chunked = cp.run_interruptible(target_s=0.0005)
+    assert float(one).hex() == float(chunked).hex()
+    cp.close()
+
+    big = load_golden("vc250_lineflow").variant("min6")  # 64 slices, ~3 s of device work
+    api = _api()
+
+    def handler(signum, frame):
+        raise TimeoutError()
+
+    old = signal.signal(signal.SIGALRM, handler)
+    signal.setitimer(signal.ITIMER_REAL, 0.3)
+    t0 = time.time()
+    try:
+        with pytest.raises(TimeoutError):
+            api.contract_sliced(big.as_execution_plan())
+    finally:
+        signal.setitimer(signal.ITIMER_REAL, 0)
+        signal.signal(signal.SIGALRM, old)
+    assert time.time() - t0 < 1.5  # interrupted after a chunk, not after all 64 slices
+
+
 def test_contract_single_network_entry():
     pp = load_golden("vc50_factorflow")
     plan = pp.as_execution_plan()
