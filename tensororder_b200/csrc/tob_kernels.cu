@@ -398,6 +398,189 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised DMMA GEMM: one producer warp streams whole 128-byte operand rows into the padded
+// K-major tiles with bulk async copies (cp.async.bulk, SASS UBLKCP) that signal a per-stage "full"
+// mbarrier by transaction bytes; eight consumer warps wait on "full", run the DMMA steps, and arrive on
+// the stage's "empty" mbarrier.  No CTA-wide barrier in the main loop (the barrier stall was the largest
+// non-math stall of k_gemm_dmma, profiles/r01c_gemm_ncu_summary.json) and no per-thread address math or
+// LDGSTS issue in the consumer warps.  Same tiling (128x64, two CTAs per SM), fragments and epilogue.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK>
+__global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParams p) {
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NC = WM * WN * 32;  // consumer threads
+    constexpr int TK = 16, LDS = TK + 4, K4 = TK / 4;
+    constexpr int WTM = TM / WM, WTN = TN / WN;
+    constexpr int MB = WTM / 8, NB = WTN / 8;
+    constexpr unsigned STAGE_BYTES = (TM + TN) * TK * 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
+    unsigned long long* cN = cM + TM;
+    unsigned long long* full = cN + TN;
+    unsigned long long* empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = p.k, ks = p.ksplit_log2;
+
+    // ---- work decode (same rasterisation as k_gemm_dmma) ----
+    const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
+    const unsigned long long tiles = tilesM * tilesN;
+    const unsigned long long id = blockIdx.x;
+    const unsigned long long split = id / tiles, tid_in = id % tiles;
+    const unsigned long long group = tilesM < 16 ? tilesM : 16;
+    const unsigned long long per_group = group * tilesN;
+    const unsigned long long gidx = tid_in / per_group, r = tid_in % per_group;
+    const unsigned long long tile_m = gidx * group + (r % group), tile_n = r / group;
+    const unsigned long long Ksplit = (1ull << k) >> ks;
+    const int KT = (int)(Ksplit / TK);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], BULK ? 1 : 32);  // bulk: the producer's expect_tx arrive + STAGE_BYTES of transactions
+            mbar_init(&empty[s], WM * WN);      // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < TM; i += NC + 32) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NC + 32) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+    __syncthreads();
+
+    if (warp == WM * WN) {
+        // ===================== producer warp =====================
+        const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
+        const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % STAGES;
+            if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);  // consumers released this slot
+            double* as = As + s * TM * LDS;
+            double* bs = Bs + s * TN * LDS;
+            if (BULK) {
+                if (lane == 0) mbar_expect_tx(&full[s], STAGE_BYTES);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < TM / 32; i++) {
+                    const int row = lane + 32 * i;
+                    bulk_copy_g2s(as + row * LDS, A + ((unsigned long long)row << k) + kt * TK, TK * 8, &full[s]);
+                }
+#pragma unroll
+                for (int i = 0; i < TN / 32; i++) {
+                    const int row = lane + 32 * i;
+                    bulk_copy_g2s(bs + row * LDS, B + ((unsigned long long)row << k) + kt * TK, TK * 8, &full[s]);
+                }
+            } else {
+                // LDGSTS from the producer warp only; the stage's "full" barrier (count 32) completes when
+                // every lane's copies have landed (cp.async.mbarrier.arrive.noinc)
+                const int chunk = lane & 7, r0 = lane >> 3;
+                const double* ag = A + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
+                const double* bg = B + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
+                const unsigned long long step = 4ull << k;
+#pragma unroll 8
+                for (int i = 0; i < TM / 4; i++) cp_async16(as + (r0 + 4 * i) * LDS + chunk * 2, ag + i * step);
+#pragma unroll 8
+                for (int i = 0; i < TN / 4; i++) cp_async16(bs + (r0 + 4 * i) * LDS + chunk * 2, bg + i * step);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&full[s]))
+                             : "memory");
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int frag_off_a = (wm * WTM + g) * LDS + t;
+    const int frag_off_b = (wn * WTN + g) * LDS + t;
+    double af[2][MB], bf[2][NB];
+    for (int kt = 0; kt < KT; kt++) {
+        const int s = kt % STAGES;
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const double* as = As + s * TM * LDS + frag_off_a;
+        const double* bs = Bs + s * TN * LDS + frag_off_b;
+#pragma unroll
+        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS];
+#pragma unroll
+        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS];
+#pragma unroll
+        for (int k4 = 0; k4 < K4; k4++) {
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < K4) {
+#pragma unroll
+                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + (k4 + 1) * 4];
+#pragma unroll
+                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + (k4 + 1) * 4];
+            }
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+        __syncwarp();                       // every lane's fragment loads of this stage have been consumed
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ---- epilogue (identical to k_gemm_dmma) ----
+    double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
+    const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+    const bool vec = (p.mask_n & 1ull) != 0;
+#pragma unroll
+    for (int i = 0; i < MB; i++) {
+        const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const int col = wn * WTN + j * 8 + 2 * t;
+            if (vec) {
+                *reinterpret_cast<double2*>(Cout + (rbase | cN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                Cout[rbase | cN[col]] = acc[i][j][0];
+                Cout[rbase | cN[col + 1]] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+template <int TM_LOG2, int TN_LOG2, int STAGES>
+constexpr size_t gemm_ws_smem_bytes() {
+    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * 20 * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16;
+}
+
 template <int TM_LOG2, int TN_LOG2, int TK, int STAGES>
 constexpr size_t gemm_smem_bytes() {
     return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (TK + 4) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
@@ -410,6 +593,8 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_77_C k_gemm_dmma<7, 7, 4, 4, 32, 3, 1>
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
+#define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true>
+#define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false>
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -422,6 +607,10 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     return e;
 }
 
@@ -536,8 +725,19 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 GEMM_77_B<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
             else
                 GEMM_77_A<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 16, 4>(), stream>>>(p);
-        } else if (op.tm_log2 == 7 && op.tn_log2 == 6)
-            GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+        } else if (op.tm_log2 == 7 && op.tn_log2 == 6) {
+            // TOB_GEMM_WS: 2 (default) = warp-specialised pipeline, producer warp issuing LDGSTS, mbarrier
+            // full/empty stages (measured +0.4 % at K=65536, +3 % at K=1024, +14 % at K=64 over the
+            // CTA-barrier pipeline); 1 = same with 128-byte bulk copies (UBLKCP: 2.4x SLOWER, the copy engine
+            // is request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
+            static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 2;
+            if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
+                GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
+            else if (ws == 2 && (op.k - op.ksplit_log2) >= 6)
+                GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
+            else
+                GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+        }
         else if (op.tm_log2 == 6 && op.tn_log2 == 6)
             GEMM_66<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
         else
