@@ -61,7 +61,7 @@ struct tob_plan {
     double slice_flops = 0;
 };
 
-static bool g_configured = false;
+static bool g_configured[64] = {false};  // per device: kernel attributes live in the device's context
 
 // ------------------------------------------------------------------------------------------------
 // Process-wide caches.  A call of B200API.contract_sliced creates, uploads, runs and destroys a plan;
@@ -193,9 +193,9 @@ static int ensure_device(int device) {
         return TOB_E_INVALID;
     }
     CUDA_TRY(cudaSetDevice(device));
-    if (!g_configured) {
+    if (device < 64 && !g_configured[device]) {
         CUDA_TRY(configure_kernels());
-        g_configured = true;
+        g_configured[device] = true;
     }
     return TOB_OK;
 }

@@ -777,12 +777,15 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
 // ------------------------------------------------------------------------------------------------
 // index permutation:  out[o] = in[sigma(o)],  address bit p of o comes from address bit src_bit[p]
 // ------------------------------------------------------------------------------------------------
-template <int EPT>  // tile elements per thread (tile = 256 * EPT elements)
-__global__ void __launch_bounds__(256) k_permute(PermuteParams p) {
+// EPT = tile elements per thread (tile = 256 * EPT elements); OFF = 32-bit element offsets when rank <= 32
+// (halves the registers held across the tile loop so 3-4 CTAs fit per SM and loads of one CTA overlap
+// the stores of another)
+template <int EPT, typename OFF>
+__global__ void __launch_bounds__(256, (EPT >= 16 ? (sizeof(OFF) == 8 ? 2 : 3) : 4)) k_permute(PermuteParams p) {
     extern __shared__ double tile[];
     const int tid = threadIdx.x;
-    unsigned long long in_off[EPT], out_off[EPT];
-    unsigned tile_idx[EPT];
+    OFF in_off[EPT], out_off[EPT];
+    unsigned short tile_idx[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
         const unsigned ei = tid + 256 * e;  // tile index, input order
@@ -794,9 +797,9 @@ __global__ void __launch_bounds__(256) k_permute(PermuteParams p) {
             ti |= (unsigned)bi << p.in_to_tile[j];
             oo |= bi << p.out_pos[j];  // the same index read in output order
         }
-        in_off[e] = io;
-        tile_idx[e] = ti;
-        out_off[e] = oo;
+        in_off[e] = (OFF)io;
+        tile_idx[e] = (unsigned short)(ti ^ (((ti >> 5) ^ (ti >> 10)) & 31u));  // XOR swizzle: strided scatters hit distinct banks
+        out_off[e] = (OFF)oo;
     }
     const unsigned long long ntiles = 1ull << p.nrest;
     for (unsigned long long tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
@@ -811,7 +814,10 @@ __global__ void __launch_bounds__(256) k_permute(PermuteParams p) {
         for (int e = 0; e < EPT; e++) tile[tile_idx[e]] = p.in[base_in | in_off[e]];
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < EPT; e++) p.out[base_out | out_off[e]] = tile[tid + 256 * e];
+        for (int e = 0; e < EPT; e++) {
+            const unsigned idx = tid + 256 * e;
+            p.out[base_out | out_off[e]] = tile[idx ^ (((idx >> 5) ^ (idx >> 10)) & 31u)];
+        }
     }
 }
 
@@ -839,11 +845,29 @@ cudaError_t launch_permute(const double* in, double* out, int rank, const int32_
         return cudaGetLastError();
     }
     // tile = low TB output bits  U  output bits fed by the low TB input bits, padded to >= 8 bits
-    const int TB = rank >= 12 ? 6 : 4;
+    static const int tb_env = getenv("TOB_PERMUTE_TB") ? atoi(getenv("TOB_PERMUTE_TB")) : 0;
+    const int TB = tb_env > 0 ? (rank >= 2 * tb_env ? tb_env : 4) : (rank >= 12 ? 6 : 4);
     bool in_tile[64] = {false};
     int tbits = 0;
     for (int q = 0; q < rank; q++)
         if (q < TB || src_bit[q] < TB) { in_tile[q] = true; tbits++; }
+    // pad to 4096-element tiles (amortises the per-tile barriers and base computation): alternately the
+    // next output bit and the output bit fed by the next input bit, so both run lengths grow
+    const int want = rank < 12 ? (rank < 8 ? rank : 8) : 12;
+    int inv[64];
+    for (int q = 0; q < rank; q++) inv[src_bit[q]] = q;  // input bit -> output bit
+    for (int step = 0, oi = TB, ii = TB; tbits < want && (oi < rank || ii < rank); step++) {
+        if ((step & 1) == 0 && oi < rank) {
+            if (!in_tile[oi]) { in_tile[oi] = true; tbits++; }
+            oi++;
+        } else if (ii < rank) {
+            if (!in_tile[inv[ii]]) { in_tile[inv[ii]] = true; tbits++; }
+            ii++;
+        } else if (oi < rank) {
+            if (!in_tile[oi]) { in_tile[oi] = true; tbits++; }
+            oi++;
+        }
+    }
     for (int q = 0; q < rank && tbits < 8; q++)
         if (!in_tile[q]) { in_tile[q] = true; tbits++; }
     // output order of the tile bits
@@ -867,15 +891,27 @@ cudaError_t launch_permute(const double* in, double* out, int rank, const int32_
     for (int q = 0; q < rank; q++)
         if (!in_tile[q]) { p.rest_out[p.nrest] = (uint8_t)q; p.rest_in[p.nrest] = (uint8_t)src_bit[q]; p.nrest++; }
     const unsigned long long ntiles = 1ull << p.nrest;
-    const unsigned blocks = (unsigned)(ntiles < 148ull * 8 ? ntiles : 148ull * 8);
+    static const int bl_env = getenv("TOB_PERMUTE_BLOCKS") ? atoi(getenv("TOB_PERMUTE_BLOCKS")) : 8;
+    const unsigned blocks = (unsigned)(ntiles < 148ull * bl_env ? ntiles : 148ull * bl_env);
     const size_t smem = ((size_t)1 << n) * 8;
-    switch (n - 8) {
-        case 0: k_permute<1><<<blocks, 256, smem, stream>>>(p); break;
-        case 1: k_permute<2><<<blocks, 256, smem, stream>>>(p); break;
-        case 2: k_permute<4><<<blocks, 256, smem, stream>>>(p); break;
-        case 3: k_permute<8><<<blocks, 256, smem, stream>>>(p); break;
-        case 4: k_permute<16><<<blocks, 256, smem, stream>>>(p); break;
-        default: return cudaErrorInvalidConfiguration;
+    if (rank <= 32) {
+        switch (n - 8) {
+            case 0: k_permute<1, unsigned><<<blocks, 256, smem, stream>>>(p); break;
+            case 1: k_permute<2, unsigned><<<blocks, 256, smem, stream>>>(p); break;
+            case 2: k_permute<4, unsigned><<<blocks, 256, smem, stream>>>(p); break;
+            case 3: k_permute<8, unsigned><<<blocks, 256, smem, stream>>>(p); break;
+            case 4: k_permute<16, unsigned><<<blocks, 256, smem, stream>>>(p); break;
+            default: return cudaErrorInvalidConfiguration;
+        }
+    } else {
+        switch (n - 8) {
+            case 0: k_permute<1, unsigned long long><<<blocks, 256, smem, stream>>>(p); break;
+            case 1: k_permute<2, unsigned long long><<<blocks, 256, smem, stream>>>(p); break;
+            case 2: k_permute<4, unsigned long long><<<blocks, 256, smem, stream>>>(p); break;
+            case 3: k_permute<8, unsigned long long><<<blocks, 256, smem, stream>>>(p); break;
+            case 4: k_permute<16, unsigned long long><<<blocks, 256, smem, stream>>>(p); break;
+            default: return cudaErrorInvalidConfiguration;
+        }
     }
     return cudaGetLastError();
 }
