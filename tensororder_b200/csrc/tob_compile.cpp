@@ -59,8 +59,10 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
         if (allow_splitk && tiles < 8 * kNumSMs) {
             // short grid: pick the power-of-two K split with the best wave efficiency (blocks / SMs
             // rounded up), keeping >= 128 K elements per split; ties go to the smaller split
+            // ... and keep the split-K partials (written once, read once: 16 * 2^(m+n+c) bytes at ~5 TB/s)
+            // below ~15 % of the join's own tensor-pipe time: 2^c <= 0.0027 * 2^k
             double best = -1.0;
-            for (int c = 0; (k - c) >= 7 && c <= 6; c++) {
+            for (int c = 0; (k - c) >= 7 && c <= 6 && std::ldexp(1.0, c) <= std::max(1.0, 0.0027 * std::ldexp(1.0, k)); c++) {
                 const double blocks = (double)(tiles << c);
                 const double waves = blocks / kNumSMs;
                 const double eff = waves / std::ceil(waves) - 0.004 * c;

@@ -28,8 +28,10 @@ def main(argv=None):
     if not hasattr(numpy, "object"):
         numpy.object = object
     from tensororder_b200.api import register
+    from tensororder_b200.slicer import register as register_slicer
 
     register()
+    register_slicer()
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
     return 0

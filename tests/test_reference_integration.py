@@ -89,3 +89,42 @@ def test_launcher_runs_the_unmodified_cli_help():
                          capture_output=True, text=True, env=env, cwd=BUILD)
     assert res.returncode == 0, res.stderr
     assert "b200" in res.stdout  # listed among the --tensor_library choices
+
+
+def test_gpu_aware_slicer_slices_less_than_the_reference_model(ref):
+    """Same plan, same byte budget: the reference cost model (out + 2*left + 2*right entries) needs more
+    slices than the executor's real arena; the count is unchanged (interpreted from the compiled program)."""
+    import math
+
+    import tensor_network
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import ref_replay
+    from conftest import load_golden
+    from program_sim import run_program
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+    from tensororder_b200.slicer import B200MemSlicer, plan_peak_bytes, register
+
+    register()
+    assert "b200_mem" in tensor_network.ALL_SLICERS
+    pp = load_golden("vc250_lineflow")
+    assert pp.expected["maxrank"] == 31
+    budget_bytes = 40e9  # between the executor's real need (30.6 GB) and the reference model's estimate (55.8 GB)
+    ref_plan = ref_replay.to_reference_plan(ref, pp)
+    assert ref_plan.memory * 8 > budget_bytes
+    tensor_network.ALL_SLICERS["greedy_mem"].slice_until(ref_plan, memory=budget_bytes / 8)
+    ours = ref_replay.to_reference_plan(ref, pp)
+    B200MemSlicer().slice_until(ours, memory=budget_bytes / 8)
+    assert plan_peak_bytes(ours) <= budget_bytes
+    assert len(ours.groups_to_slice) == 0 < len(ref_plan.groups_to_slice)
+    # a budget that needs real slicing: still met, with at most as many slices as the reference model asks for
+    tight = 8e9
+    a = ref_replay.to_reference_plan(ref, pp)
+    tensor_network.ALL_SLICERS["greedy_mem"].slice_until(a, memory=tight / 8)
+    b = ref_replay.to_reference_plan(ref, pp)
+    B200MemSlicer().slice_until(b, memory=tight / 8)
+    assert plan_peak_bytes(b) <= tight and 0 < len(b.groups_to_slice) <= len(a.groups_to_slice)
+    pp = load_golden("vc100_lineflow")
+    with pytest.raises(RuntimeError):
+        B200MemSlicer().slice_until(ref_replay.to_reference_plan(ref, pp), memory=16)  # 128 bytes: impossible
