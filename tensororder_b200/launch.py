@@ -32,6 +32,16 @@ def main(argv=None):
 
     register()
     register_slicer()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # launched by torchrun: one process per GPU; B200API shards the slices r::W and all-reduces the count
+        import torch
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        if dist.get_rank() != 0:
+            sys.stdout = open(os.devnull, "w")  # every rank computes the same Count; rank 0 reports it
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
     return 0
