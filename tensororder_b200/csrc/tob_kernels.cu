@@ -436,11 +436,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK>
+// SWZ: dense 128-byte rows with the 16-byte chunk index XOR-ed by ((row & 3) << 1) instead of the padded
+// 160-byte rows: the 8x4 fragment loads stay conflict-free and a stage shrinks from 30 KB to 24 KB, so FOUR
+// stages fit twice per SM (ncu showed consumers waiting on `full` 24 % of the time with three).
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK, bool SWZ>
 __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NC = WM * WN * 32;  // consumer threads
-    constexpr int TK = 16, LDS = TK + 4, K4 = TK / 4;
+    constexpr int TK = 16, LDS = SWZ ? TK : TK + 4, K4 = TK / 4;
+    static_assert(!(BULK && SWZ), "bulk row copies cannot swizzle");
     constexpr int WTM = TM / WM, WTN = TN / WN;
     constexpr int MB = WTM / 8, NB = WTN / 8;
     constexpr unsigned STAGE_BYTES = (TM + TN) * TK * 8;
@@ -503,14 +507,15 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
             } else {
                 // LDGSTS from the producer warp only; the stage's "full" barrier (count 32) completes when
                 // every lane's copies have landed (cp.async.mbarrier.arrive.noinc)
-                const int chunk = lane & 7, r0 = lane >> 3;
+                const int chunk = lane & 7, r0 = lane >> 3;  // r0 = row & 3 for every row this lane copies
                 const double* ag = A + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
                 const double* bg = B + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
                 const unsigned long long step = 4ull << k;
+                const int dchunk = SWZ ? (chunk ^ (r0 << 1)) : chunk;
 #pragma unroll 8
-                for (int i = 0; i < TM / 4; i++) cp_async16(as + (r0 + 4 * i) * LDS + chunk * 2, ag + i * step);
+                for (int i = 0; i < TM / 4; i++) cp_async16(as + (r0 + 4 * i) * LDS + dchunk * 2, ag + i * step);
 #pragma unroll 8
-                for (int i = 0; i < TN / 4; i++) cp_async16(bs + (r0 + 4 * i) * LDS + chunk * 2, bg + i * step);
+                for (int i = 0; i < TN / 4; i++) cp_async16(bs + (r0 + 4 * i) * LDS + dchunk * 2, bg + i * step);
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&full[s]))
                              : "memory");
             }
@@ -526,8 +531,12 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
     for (int i = 0; i < MB; i++)
 #pragma unroll
         for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int frag_off_a = (wm * WTM + g) * LDS + t;
-    const int frag_off_b = (wn * WTN + g) * LDS + t;
+    const int frag_off_a = (wm * WTM + g) * LDS;
+    const int frag_off_b = (wn * WTN + g) * LDS;
+    int koff[K4];  // column of fragment element (k4, t) inside a tile row
+#pragma unroll
+    for (int k4 = 0; k4 < K4; k4++)
+        koff[k4] = SWZ ? ((((2 * k4 + (t >> 1)) ^ ((g & 3) << 1)) << 1) + (t & 1)) : (k4 * 4 + t);
     double af[2][MB], bf[2][NB];
     for (int kt = 0; kt < KT; kt++) {
         const int s = kt % STAGES;
@@ -535,17 +544,17 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
         const double* as = As + s * TM * LDS + frag_off_a;
         const double* bs = Bs + s * TN * LDS + frag_off_b;
 #pragma unroll
-        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS];
+        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS + koff[0]];
 #pragma unroll
-        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS];
+        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS + koff[0]];
 #pragma unroll
         for (int k4 = 0; k4 < K4; k4++) {
             const int cur = k4 & 1, nxt = cur ^ 1;
             if (k4 + 1 < K4) {
 #pragma unroll
-                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + (k4 + 1) * 4];
+                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + koff[(k4 + 1) % K4]];
 #pragma unroll
-                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + (k4 + 1) * 4];
+                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + koff[(k4 + 1) % K4]];
             }
 #pragma unroll
             for (int i = 0; i < MB; i++)
@@ -576,9 +585,9 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
     }
 }
 
-template <int TM_LOG2, int TN_LOG2, int STAGES>
+template <int TM_LOG2, int TN_LOG2, int STAGES, bool SWZ = false>
 constexpr size_t gemm_ws_smem_bytes() {
-    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * 20 * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16;
+    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (SWZ ? 16 : 20) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16;
 }
 
 template <int TM_LOG2, int TN_LOG2, int TK, int STAGES>
@@ -593,8 +602,9 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_77_C k_gemm_dmma<7, 7, 4, 4, 32, 3, 1>
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
-#define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true>
-#define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false>
+#define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true, false>
+#define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
+#define GEMM_76_WZ k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true>
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -611,6 +621,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_WS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WZ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     return e;
 }
 
@@ -733,7 +745,10 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 2;
             if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
                 GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
-            else if (ws == 2 && (op.k - op.ksplit_log2) >= 6)
+            else if ((ws == 3 || (ws == 2 && (op.k - op.ksplit_log2) >= 8)) && (op.k - op.ksplit_log2) >= 6)
+                // swizzled dense rows, 4 stages: +0.2 % (K=65536) .. +1.5 % (K=1024) over the padded 3-stage ring
+                GEMM_76_WZ<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
+            else if (ws >= 2 && (op.k - op.ksplit_log2) >= 6)
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else
                 GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
