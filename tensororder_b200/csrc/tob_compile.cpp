@@ -56,7 +56,9 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
         if (gemm_variant() == 3 && op->tn_log2 == 7) op->tn_log2 = 6;
         int64_t tiles = (int64_t)1 << ((m - op->tm_log2) + (n - op->tn_log2));
         int ks = 0;
-        if (allow_splitk && tiles < 8 * kNumSMs) {
+        // concurrent CTA slots: the 128x64 kernels run two CTAs per SM
+        const int slots = kNumSMs * ((op->tm_log2 == 7 && op->tn_log2 == 6) ? 2 : 1);
+        if (allow_splitk && tiles < 8 * slots) {
             // short grid: pick the power-of-two K split with the best wave efficiency (blocks / SMs
             // rounded up), keeping >= 128 K elements per split; ties go to the smaller split
             // ... and keep the split-K partials (written once, read once: 16 * 2^(m+n+c) bytes at ~5 TB/s)
@@ -64,7 +66,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
             double best = -1.0;
             for (int c = 0; (k - c) >= 7 && c <= 6 && std::ldexp(1.0, c) <= std::max(1.0, 0.0027 * std::ldexp(1.0, k)); c++) {
                 const double blocks = (double)(tiles << c);
-                const double waves = blocks / kNumSMs;
+                const double waves = blocks / slots;
                 const double eff = waves / std::ceil(waves) - 0.004 * c;
                 if (eff > best + 1e-9) { best = eff; ks = c; }
             }

@@ -38,6 +38,7 @@ CASES = [
     (9, 9, 5), (14, 14, 14), (20, 20, 20), (16, 10, 8), (15, 13, 7), (13, 14, 6), (14, 12, 4),
     (18, 16, 9), (17, 17, 10), (20, 12, 6), (21, 18, 9), (13, 13, 1), (12, 12, 0), (22, 8, 8),
     (12, 11, 2), (11, 13, 3), (14, 10, 3), (16, 3, 1), (17, 2, 0),  # small-k GEMM (zero-filled K step) and x4 streaming kernel
+    (14, 14, 8), (15, 14, 8), (16, 16, 10), (22, 22, 16),  # 64x64 tiles, 128x64 tiles, split-K with few tiles
 ]
 
 
