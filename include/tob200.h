@@ -71,7 +71,8 @@ typedef struct {
     int64_t mem_limit_bytes; /* 0: use free device memory; else refuse (TOB_E_OOM) plans needing more      */
     int32_t use_microtree;   /* 1 (default): subtrees made only of tiny joins run inside ONE kernel launch  */
                              /* (one CTA per subtree); 0: one launch per join                              */
-    int32_t reserved;
+    int32_t slice_lanes;     /* slices in flight at once, each with its own arena/workspace/stream:        */
+                             /* 0 (default) = 2 when the second arena costs <= 2 GiB, else 1; 1; 2          */
 } tob_options;
 
 void tob_default_options(tob_options* opt);

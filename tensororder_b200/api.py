@@ -43,7 +43,8 @@ class CompiledPlan:
     """Owns one `tob_plan` (device arena, leaf tensors, CUDA graph)."""
 
     def __init__(self, flat: FlatPlan, device: int = 0, use_graph=None, kernel_policy: int = 0,
-                 hoist_invariant: bool = True, mem_limit_bytes: int = 0, use_microtree: bool = True):
+                 hoist_invariant: bool = True, mem_limit_bytes: int = 0, use_microtree: bool = True,
+                 slice_lanes: int = 0):
         self.flat = flat
         self._handle = c_void_p()
         desc = cabi.tob_plan_desc()
@@ -67,6 +68,7 @@ class CompiledPlan:
         opt.hoist_invariant = 1 if hoist_invariant else 0
         opt.mem_limit_bytes = int(mem_limit_bytes)
         opt.use_microtree = 1 if use_microtree else 0
+        opt.slice_lanes = int(slice_lanes)
         rc = cabi.lib.tob_plan_create(byref(desc), byref(opt), byref(self._handle))
         if rc != cabi.TOB_OK:
             raise ValueError("tob_plan_create: " + cabi.last_error())
@@ -191,6 +193,7 @@ class B200API:
         self._kernel_policy = 0
         self._hoist = True
         self._microtree = True
+        self._lanes = 0
         self._distributed = True
         self.last_stats = {}
 
@@ -210,6 +213,8 @@ class B200API:
             self._kernel_policy = int(value)
         elif key == "hoist_invariant":
             self._hoist = bool(value)
+        elif key == "slice_lanes":
+            self._lanes = int(value)
         elif key == "use_microtree":
             self._microtree = bool(value)
         elif key == "distributed":
@@ -239,7 +244,7 @@ class B200API:
         rank, world = self._rank_world()
         compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
                                 kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
-                                use_microtree=self._microtree)
+                                use_microtree=self._microtree, slice_lanes=self._lanes)
         try:
             t1 = time.perf_counter()
             compiled.upload()

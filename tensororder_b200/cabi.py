@@ -37,7 +37,7 @@ class tob_options(ctypes.Structure):
         ("hoist_invariant", c_int32),
         ("mem_limit_bytes", c_int64),
         ("use_microtree", c_int32),
-        ("reserved", c_int32),
+        ("slice_lanes", c_int32),
     ]
 
 

@@ -335,7 +335,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         NodeInfo& X = P->nodes[i];
         size_of[i] = (int64_t)1 << (op.m + op.n);
         op.c_offset = arena.alloc(size_of[i]);
-        X.where.space = 1;
+        X.where.space = persistent[i] ? 2 : 1;  // hoisted results are read by every lane from lane 0's arena
         X.where.offset = op.c_offset;
         X.where.leaf = -1;
         X.where.node = i;
@@ -434,6 +434,11 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     P->slice_ops.push_back(acc);
     P->arena_doubles = arena.top;
     P->ws_doubles = ws_max;
+    // Two slices in flight (own arena + workspace + stream each) when that costs at most 2 GiB extra: the
+    // launch-bound stretches of one slice then overlap the GEMMs of the other.  opt.slice_lanes: 0 auto, 1, 2.
+    const int want_lanes = opt.slice_lanes;
+    const bool cheap = (P->arena_doubles + P->ws_doubles) * 8 <= ((int64_t)2 << 30);
+    P->lanes = (S > 0 && (want_lanes == 2 || (want_lanes == 0 && cheap))) ? 2 : 1;
     return TOB_OK;
 }
 
@@ -470,7 +475,7 @@ std::string describe(const Program& P) {
         }
         o << "]";
     };
-    o << "{\"n_slice_groups\":" << P.n_slice_groups << ",\"leaf_doubles\":" << P.leaf_doubles
+    o << "{\"n_slice_groups\":" << P.n_slice_groups << ",\"lanes\":" << P.lanes << ",\"leaf_doubles\":" << P.leaf_doubles
       << ",\"arena_doubles\":" << P.arena_doubles << ",\"ws_doubles\":" << P.ws_doubles
       << ",\"total_flops\":" << P.total_flops << ",\"total_bytes\":" << P.total_bytes << ",\"leaves\":[";
     for (size_t l = 0; l < P.leaves.size(); l++) {

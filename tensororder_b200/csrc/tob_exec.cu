@@ -26,19 +26,34 @@ using namespace tob;
         }                                                                                     \
     } while (0)
 
+constexpr int kMaxLanes = 2;        // slices in flight at once (each lane: own arena, workspace, stream)
+constexpr int kMaxResults = 4096;   // per-slice results buffered on the device before the ordered sum
+
+struct Lane {
+    cudaStream_t stream = nullptr;  // lane 0: the plan's stream (own or caller's); lane >= 1: own stream
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // lane 0: run start / end;  lane >= 1: fork / done
+    double* d_arena = nullptr;
+    double* d_ws = nullptr;
+    long long* d_leaf_off = nullptr;
+    DevState* d_state = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+};
+
 struct tob_plan {
     Program prog;
     bool uploaded = false;
     int device = 0;
-    cudaStream_t stream = nullptr;      // the stream runs are issued on (own or caller's)
-    cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // one device block: [state | leaf_off | slice tables | micro programs | leaves | arena | workspace]
+    int n_lanes = 1;
+    Lane lane[kMaxLanes];
+    // one device block: [states | acc | results | leaf_off x lanes | slice tables | micro programs | leaves |
+    //                    arena x lanes | workspace x lanes]
     void* d_block = nullptr;
     size_t d_block_size = 0;
-    double *d_leaves = nullptr, *d_arena = nullptr, *d_ws = nullptr;
-    DevState* d_state = nullptr;
-    long long* d_leaf_off = nullptr;
+    double* d_leaves = nullptr;
+    double* d_acc = nullptr;
+    double* d_results = nullptr;
     int32_t* d_term_start = nullptr;
     uint8_t *d_id_bit = nullptr, *d_addr_bit = nullptr;
     MicroOpDev* d_micro_ops[2] = {nullptr, nullptr};
@@ -46,16 +61,15 @@ struct tob_plan {
     // one pinned block mirroring the prefix of the device block up to the end of the leaves
     void* h_block = nullptr;
     size_t h_block_size = 0;
-    DevState* h_state = nullptr;     // upload slot
-    DevState* h_readback = nullptr;  // result slot
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    DevState* h_state = nullptr;   // upload slots, one per lane
+    double* h_readback = nullptr;  // result slot
     bool has_terms = false;
     double last_ms = 0;
     int64_t last_launches = 0;
     int64_t graph_launches_per_slice = 0;
     int64_t runs = 0;
     std::vector<cudaEvent_t> gemm_events;  // pairs
+    std::vector<double> gemm_event_flops;
     double last_gemm_ms = 0, last_gemm_flops = 0;
     int64_t last_gemm_launches = 0;
     double slice_flops = 0;
@@ -209,7 +223,7 @@ void tob_default_options(tob_options* opt) {
     opt->hoist_invariant = 1;
     opt->mem_limit_bytes = 0;
     opt->use_microtree = 1;
-    opt->reserved = 0;
+    opt->slice_lanes = 0;
 }
 
 const char* tob_last_error(void) { return g_error.c_str(); }
@@ -241,7 +255,9 @@ int64_t tob_plan_peak_bytes(const tob_plan* p) {
     size_t tables = 4096 + 32 * p->prog.leaves.size();
     for (int w = 0; w < 2; w++) tables += p->prog.micro[w].ops.size() * sizeof(MicroOpDev) + p->prog.micro[w].cta_start.size() * 4 + 1024;
     for (const LeafInfo& L : p->prog.leaves) tables += 2 * L.slice_id_bit.size();
-    return 8 * (p->prog.leaf_doubles + p->prog.arena_doubles + p->prog.ws_doubles) + (int64_t)tables;
+    tables += kMaxResults * 8;
+    const int64_t lanes = p->prog.lanes;
+    return 8 * (p->prog.leaf_doubles + lanes * (p->prog.arena_doubles + p->prog.ws_doubles)) + (int64_t)tables;
 }
 
 uint64_t tob_plan_num_slices(const tob_plan* p) { return (uint64_t)1 << p->prog.n_slice_groups; }
@@ -259,28 +275,29 @@ int64_t tob_plan_describe(const tob_plan* p, char* buf, int64_t cap) {
 int64_t tob_plan_num_ops(const tob_plan* p) { return (int64_t)(p->prog.invariant_ops.size() + p->prog.slice_ops.size()); }
 
 static void release_device(tob_plan* p) {
-    if (p->own_stream) cudaStreamSynchronize(p->own_stream);
-    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
-    if (p->graph) cudaGraphDestroy(p->graph);
-    p->graph_exec = nullptr;
-    p->graph = nullptr;
+    for (int l = 0; l < kMaxLanes; l++) {
+        Lane& L = p->lane[l];
+        if (L.own_stream) cudaStreamSynchronize(L.own_stream);
+        if (L.graph_exec) cudaGraphExecDestroy(L.graph_exec);
+        if (L.graph) cudaGraphDestroy(L.graph);
+        if (L.own_stream) streams_release(StreamSet{L.own_stream, L.ev_a, L.ev_b, p->device});
+        L = Lane();
+    }
     pool_release(Block{p->d_block, p->d_block_size, p->device, false});
     pool_release(Block{p->h_block, p->h_block_size, p->device, true});
-    streams_release(StreamSet{p->own_stream, p->ev0, p->ev1, p->device});
     for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
     p->gemm_events.clear();
-    p->d_block = nullptr; p->h_block = nullptr; p->d_state = nullptr; p->d_leaf_off = nullptr;
+    p->d_block = nullptr; p->h_block = nullptr;
     p->d_term_start = nullptr; p->d_id_bit = nullptr; p->d_addr_bit = nullptr;
     p->h_state = nullptr; p->h_readback = nullptr;
     for (int w = 0; w < 2; w++) { p->d_micro_ops[w] = nullptr; p->d_micro_start[w] = nullptr; }
-    p->own_stream = nullptr; p->ev0 = p->ev1 = nullptr; p->stream = nullptr;
     p->uploaded = false;
     p->runs = 0;
 }
 
 void tob_plan_destroy(tob_plan* p) {
     if (!p) return;
-    if (p->uploaded || p->own_stream) {
+    if (p->uploaded || p->lane[0].own_stream) {
         cudaSetDevice(p->device);
         release_device(p);
     }
@@ -299,7 +316,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     if (n_doubles != G.src_leaf_len) { set_error("leaf buffer length does not match the plan"); return TOB_E_INVALID; }
     int rc = ensure_device(p->device);
     if (rc != TOB_OK) return rc;
-    if (p->uploaded || p->own_stream) release_device(p);
+    if (p->uploaded || p->lane[0].own_stream) release_device(p);
 
     const int64_t need = tob_plan_peak_bytes(p);
     if (G.opt.mem_limit_bytes > 0 && need > G.opt.mem_limit_bytes) {
@@ -307,12 +324,15 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         return TOB_E_OOM;
     }
     const double t_dev = now_ms();
-    StreamSet ss;
-    CUDA_TRY(streams_acquire(p->device, &ss));
-    p->own_stream = ss.stream;
-    p->stream = ss.stream;
-    p->ev0 = ss.ev0;
-    p->ev1 = ss.ev1;
+    p->n_lanes = G.lanes;
+    for (int l = 0; l < p->n_lanes; l++) {
+        StreamSet ss;
+        CUDA_TRY(streams_acquire(p->device, &ss));
+        p->lane[l].own_stream = ss.stream;
+        p->lane[l].stream = ss.stream;
+        p->lane[l].ev_a = ss.ev0;
+        p->lane[l].ev_b = ss.ev1;
+    }
     p->slice_flops = 0;
     for (const Op& op : G.slice_ops) p->slice_flops += op.flops;
 
@@ -333,8 +353,12 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     // ---- layout of the single device block (byte offsets, 256-B aligned sections) ----
     size_t off = 0;
     auto section = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_state = section(sizeof(DevState));
-    const size_t o_leaf_off = section(sizeof(long long) * (L + 1));
+    const int NL = p->n_lanes;
+    const size_t o_state = section(sizeof(DevState) * kMaxLanes);
+    const size_t o_acc = section(64);
+    const size_t o_results = section(sizeof(double) * kMaxResults);
+    size_t o_leaf_off[kMaxLanes];
+    for (int l = 0; l < NL; l++) o_leaf_off[l] = section(sizeof(long long) * (L + 1));
     const size_t o_term = section(sizeof(int32_t) * (L + 1));
     const size_t o_idb = section(id_bit.size() + 1);
     const size_t o_adb = section(addr_bit.size() + 1);
@@ -345,8 +369,9 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     }
     const size_t o_leaves = section((size_t)G.leaf_doubles * 8);
     const size_t prefix_bytes = off;  // everything up to here is initialised from the pinned mirror
-    const size_t o_arena = section((size_t)G.arena_doubles * 8);
-    const size_t o_ws = section((size_t)G.ws_doubles * 8);
+    size_t o_arena[kMaxLanes], o_ws[kMaxLanes];
+    for (int l = 0; l < NL; l++) o_arena[l] = section((size_t)G.arena_doubles * 8);
+    for (int l = 0; l < NL; l++) o_ws[l] = section((size_t)G.ws_doubles * 8);
     const size_t total_bytes = off + 256;
 
     const double t_tables = now_ms();
@@ -358,8 +383,10 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             set_error("plan needs " + std::to_string(total_bytes) + " bytes, device has " + std::to_string(free_b) + " free");
-            streams_release(ss);
-            p->own_stream = nullptr; p->stream = nullptr; p->ev0 = p->ev1 = nullptr;
+            for (int l = 0; l < p->n_lanes; l++) {
+                streams_release(StreamSet{p->lane[l].own_stream, p->lane[l].ev_a, p->lane[l].ev_b, p->device});
+                p->lane[l] = Lane();
+            }
             return TOB_E_OOM;
         }
         CUDA_TRY(e);
@@ -371,8 +398,14 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     p->h_block_size = hb.size;
     char* d = static_cast<char*>(p->d_block);
     char* h = static_cast<char*>(p->h_block);
-    p->d_state = reinterpret_cast<DevState*>(d + o_state);
-    p->d_leaf_off = reinterpret_cast<long long*>(d + o_leaf_off);
+    for (int l = 0; l < NL; l++) {
+        p->lane[l].d_state = reinterpret_cast<DevState*>(d + o_state) + l;
+        p->lane[l].d_leaf_off = reinterpret_cast<long long*>(d + o_leaf_off[l]);
+        p->lane[l].d_arena = reinterpret_cast<double*>(d + o_arena[l]);
+        p->lane[l].d_ws = reinterpret_cast<double*>(d + o_ws[l]);
+    }
+    p->d_acc = reinterpret_cast<double*>(d + o_acc);
+    p->d_results = reinterpret_cast<double*>(d + o_results);
     p->d_term_start = reinterpret_cast<int32_t*>(d + o_term);
     p->d_id_bit = reinterpret_cast<uint8_t*>(d + o_idb);
     p->d_addr_bit = reinterpret_cast<uint8_t*>(d + o_adb);
@@ -381,10 +414,8 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         p->d_micro_start[w] = reinterpret_cast<int32_t*>(d + o_mstart[w]);
     }
     p->d_leaves = reinterpret_cast<double*>(d + o_leaves);
-    p->d_arena = reinterpret_cast<double*>(d + o_arena);
-    p->d_ws = reinterpret_cast<double*>(d + o_ws);
     p->h_state = reinterpret_cast<DevState*>(h + o_state);
-    p->h_readback = reinterpret_cast<DevState*>(h + prefix_bytes);
+    p->h_readback = reinterpret_cast<double*>(h + prefix_bytes);
 
     const double t_alloc = now_ms();
     // ---- fill the pinned mirror: tables, micro programs, leaves permuted into canonical order ----
@@ -424,8 +455,8 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     }
     const double t_fill = now_ms();
     // ---- ONE pinned host->device copy: state, tables, micro programs, leaves ----
-    CUDA_TRY(cudaMemcpyAsync(p->d_block, p->h_block, prefix_bytes, cudaMemcpyHostToDevice, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_block, p->h_block, prefix_bytes, cudaMemcpyHostToDevice, p->lane[0].stream));
+    CUDA_TRY(cudaStreamSynchronize(p->lane[0].stream));
     if (trace)
         fprintf(stderr, "[tob] upload: ensure_device %.3f  streams+tables %.3f  alloc %.3f  fill %.3f  h2d+sync %.3f ms (%zu B)\n",
                 t_dev - t_begin, t_tables - t_dev, t_alloc - t_tables, t_fill - t_alloc, now_ms() - t_fill, prefix_bytes);
@@ -433,15 +464,20 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     return TOB_OK;
 }
 
-static KParams make_params(const tob_plan* p, const Op& op) {
+static const double* operand_ptr(const tob_plan* p, const Lane& L, const OperandRef& r) {
+    // space 0: leaf region; 1: this lane's arena; 2: slice-invariant tensor, always in lane 0's arena
+    const double* base = r.space == 0 ? p->d_leaves : (r.space == 2 ? p->lane[0].d_arena : L.d_arena);
+    return base + r.offset;
+}
+
+static KParams make_params(const tob_plan* p, const Lane& L, const Op& op) {
     KParams k;
     memset(&k, 0, sizeof(k));
-    auto base = [&](const OperandRef& r) -> const double* { return (r.space == 0 ? p->d_leaves : p->d_arena) + r.offset; };
-    k.a = base(op.a);
-    k.b = base(op.b);
-    k.c = p->d_arena + op.c_offset;
-    k.ws = p->d_ws;
-    k.leaf_off = p->d_leaf_off;
+    k.a = operand_ptr(p, L, op.a);
+    k.b = operand_ptr(p, L, op.b);
+    k.c = L.d_arena + op.c_offset;
+    k.ws = L.d_ws;
+    k.leaf_off = L.d_leaf_off;
     k.a_leaf = op.a.leaf;
     k.b_leaf = op.b.leaf;
     k.m = op.m;
@@ -456,32 +492,33 @@ static KParams make_params(const tob_plan* p, const Op& op) {
     return k;
 }
 
-static cudaError_t launch_op(tob_plan* p, const Op& op, int* launches) {
+static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* launches) {
     if (op.kind == OP_ACCUM) {
-        const double* root = (op.a.space == 0 ? p->d_leaves : p->d_arena) + op.a.offset;
         (*launches)++;
-        return launch_accum(p->d_state, root, p->d_leaf_off, op.a.leaf, p->stream);
+        return launch_accum(L.d_state, operand_ptr(p, L, op.a), L.d_leaf_off, op.a.leaf, p->d_results, L.stream);
     }
     if (op.kind == OP_MICRO) {
         const int w = op.micro_which;
         (*launches)++;
         return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)p->prog.micro[w].cta_start.size() - 1,
-                                p->d_leaves, p->d_arena, p->d_leaf_off, p->stream);
+                                p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, L.stream);
     }
-    KParams k = make_params(p, op);
-    return launch_contract(op, k, p->stream, launches);
+    KParams k = make_params(p, L, op);
+    return launch_contract(op, k, L.stream, launches);
 }
 
-static cudaError_t launch_slice(tob_plan* p, int* launches) {
-    cudaError_t e;
-    if (p->has_terms) {
-        SliceTables t{p->d_term_start, p->d_id_bit, p->d_addr_bit, p->d_leaf_off, (int32_t)p->prog.leaves.size()};
-        e = launch_begin_slice(p->d_state, t, p->stream);
-        (*launches)++;
-        if (e != cudaSuccess) return e;
-    }
+static cudaError_t launch_begin(tob_plan* p, const Lane& L, int* launches) {
+    if (!p->has_terms) return cudaSuccess;
+    SliceTables t{p->d_term_start, p->d_id_bit, p->d_addr_bit, L.d_leaf_off, (int32_t)p->prog.leaves.size()};
+    (*launches)++;
+    return launch_begin_slice(L.d_state, t, L.stream);
+}
+
+static cudaError_t launch_slice(tob_plan* p, const Lane& L, int* launches) {
+    cudaError_t e = launch_begin(p, L, launches);
+    if (e != cudaSuccess) return e;
     for (const Op& op : p->prog.slice_ops) {
-        e = launch_op(p, op, launches);
+        e = launch_op(p, L, op, launches);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -503,23 +540,17 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     int rc = ensure_device(p->device);
     if (rc != TOB_OK) return rc;
     int launches = 0;
-    p->h_state->next_slice = first;
-    p->h_state->stride = stride;
-    p->h_state->acc = initial;
-    p->h_state->pad = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(p->d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, p->stream));
-    CUDA_TRY(cudaEventRecord(p->ev0, p->stream));
-    const bool skip_invariant = (flags & TOB_RUN_SKIP_INVARIANT) != 0 && p->runs > 0;
+    Lane& L0 = p->lane[0];
     const int ug = p->prog.opt.use_graph;
     // auto: launch-bound slices replay as a graph, but only once the plan is being reused (second run or
     // several slices): a plan that runs a single slice once never pays capture + instantiate
     const bool as_graph = (ug == 1) || (ug == 2 && p->slice_flops < 2e9 && (p->runs > 0 || count >= 4));
+    const bool skip_invariant = (flags & TOB_RUN_SKIP_INVARIANT) != 0 && p->runs > 0;
     size_t n_gemm = 0;
-    double gemm_flops = 0;
     // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py)
-    auto timed_op = [&](const Op& op) -> int {
+    auto timed_op = [&](const Lane& L, const Op& op) -> int {
         if (op.kind != OP_GEMM || as_graph) {
-            CUDA_TRY(launch_op(p, op, &launches));
+            CUDA_TRY(launch_op(p, L, op, &launches));
             return TOB_OK;
         }
         if (p->gemm_events.size() < 2 * (n_gemm + 1)) {
@@ -528,63 +559,92 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
             CUDA_TRY(cudaEventCreate(&b));
             p->gemm_events.push_back(a);
             p->gemm_events.push_back(b);
+            p->gemm_event_flops.push_back(0.0);
         }
-        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm], p->stream));
-        CUDA_TRY(launch_op(p, op, &launches));
-        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm + 1], p->stream));
+        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm], L.stream));
+        CUDA_TRY(launch_op(p, L, op, &launches));
+        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm + 1], L.stream));
+        p->gemm_event_flops[n_gemm] = op.flops;
         n_gemm++;
-        gemm_flops += op.flops;
         return TOB_OK;
     };
-    if (count > 0) {
-        if (!skip_invariant)
+
+    CUDA_TRY(cudaEventRecord(L0.ev_a, L0.stream));
+    uint64_t done = 0;
+    bool first_batch = true;
+    do {
+        const uint64_t batch = std::min<uint64_t>(count - done, kMaxResults);
+        if (!first_batch) CUDA_TRY(cudaStreamSynchronize(L0.stream));  // the pinned state slots are about to be rewritten
+        const int lanes = (int)std::min<uint64_t>((uint64_t)p->n_lanes, std::max<uint64_t>(batch, 1));
+        for (int l = 0; l < lanes; l++) {
+            p->h_state[l].next_slice = first + (done + l) * stride;
+            p->h_state[l].stride = stride * lanes;
+            p->h_state[l].slot = l;
+            p->h_state[l].slot_stride = lanes;
+        }
+        CUDA_TRY(cudaMemcpyAsync(L0.d_state, p->h_state, sizeof(DevState) * lanes, cudaMemcpyHostToDevice, L0.stream));
+        if (first_batch && batch > 0 && !skip_invariant)
             for (const Op& op : p->prog.invariant_ops) {
-                int rc2 = timed_op(op);
+                int rc2 = timed_op(L0, op);
                 if (rc2 != TOB_OK) return rc2;
             }
+        // fork: the other lanes start after the state upload and the slice-invariant prologue
+        for (int l = 1; l < lanes; l++) {
+            CUDA_TRY(cudaEventRecord(p->lane[l].ev_a, L0.stream));
+            CUDA_TRY(cudaStreamWaitEvent(p->lane[l].stream, p->lane[l].ev_a, 0));
+        }
         if (as_graph) {
-            if (!p->graph_exec) {
+            for (int l = 0; l < lanes; l++) {
+                Lane& L = p->lane[l];
+                if (L.graph_exec) continue;
                 int per_slice = 0;
-                CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-                cudaError_t e = launch_slice(p, &per_slice);
-                cudaError_t e2 = cudaStreamEndCapture(p->stream, &p->graph);
+                CUDA_TRY(cudaStreamBeginCapture(L.stream, cudaStreamCaptureModeThreadLocal));
+                cudaError_t e = launch_slice(p, L, &per_slice);
+                cudaError_t e2 = cudaStreamEndCapture(L.stream, &L.graph);
                 CUDA_TRY(e);
                 CUDA_TRY(e2);
-                CUDA_TRY(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+                CUDA_TRY(cudaGraphInstantiate(&L.graph_exec, L.graph, 0));
                 p->graph_launches_per_slice = per_slice;
             }
-            for (uint64_t s = 0; s < count; s++) CUDA_TRY(cudaGraphLaunch(p->graph_exec, p->stream));
-            launches += (int)(p->graph_launches_per_slice * count);
+            for (uint64_t j = 0; j < batch; j++) CUDA_TRY(cudaGraphLaunch(p->lane[j % lanes].graph_exec, p->lane[j % lanes].stream));
+            launches += (int)(p->graph_launches_per_slice * batch);
         } else {
-            for (uint64_t s = 0; s < count; s++) {
-                if (p->has_terms) {
-                    SliceTables t{p->d_term_start, p->d_id_bit, p->d_addr_bit, p->d_leaf_off, (int32_t)p->prog.leaves.size()};
-                    CUDA_TRY(launch_begin_slice(p->d_state, t, p->stream));
-                    launches++;
-                }
+            for (uint64_t j = 0; j < batch; j++) {
+                const Lane& L = p->lane[j % lanes];
+                CUDA_TRY(launch_begin(p, L, &launches));
                 for (const Op& op : p->prog.slice_ops) {
-                    int rc2 = timed_op(op);
+                    int rc2 = timed_op(L, op);
                     if (rc2 != TOB_OK) return rc2;
                 }
             }
         }
-    }
-    CUDA_TRY(cudaEventRecord(p->ev1, p->stream));
-    CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+        // join, then the ordered sum of this batch's per-slice results (sequential, slice order)
+        for (int l = 1; l < lanes; l++) {
+            CUDA_TRY(cudaEventRecord(p->lane[l].ev_b, p->lane[l].stream));
+            CUDA_TRY(cudaStreamWaitEvent(L0.stream, p->lane[l].ev_b, 0));
+        }
+        CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, (int)batch, initial, first_batch ? 0 : 1, L0.stream));
+        launches++;
+        done += batch;
+        first_batch = false;
+    } while (done < count);
+    CUDA_TRY(cudaEventRecord(L0.ev_b, L0.stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_acc, sizeof(double), cudaMemcpyDeviceToHost, L0.stream));
+    CUDA_TRY(cudaStreamSynchronize(L0.stream));
     float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, L0.ev_a, L0.ev_b));
     p->last_ms = ms;
     p->last_launches = launches;
     p->last_gemm_ms = 0;
+    p->last_gemm_flops = 0;
     for (size_t i = 0; i < n_gemm; i++) {
         float g = 0;
         CUDA_TRY(cudaEventElapsedTime(&g, p->gemm_events[2 * i], p->gemm_events[2 * i + 1]));
         p->last_gemm_ms += g;
+        p->last_gemm_flops += p->gemm_event_flops[i];
     }
-    p->last_gemm_flops = gemm_flops;
     p->last_gemm_launches = (int64_t)n_gemm;
-    *result = p->h_readback->acc;
+    *result = *p->h_readback;
     p->runs++;
     return TOB_OK;
 }
@@ -599,9 +659,10 @@ int tob_plan_last_gemm(const tob_plan* p, double* ms, double* flops, int64_t* la
 
 int tob_plan_set_stream(tob_plan* p, void* stream) {
     if (!p || !p->uploaded) { set_error("tob_plan_set_stream: plan is not uploaded"); return TOB_E_INVALID; }
-    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
-    if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
-    p->stream = stream ? (cudaStream_t)stream : p->own_stream;
+    Lane& L0 = p->lane[0];
+    if (L0.graph_exec) { cudaGraphExecDestroy(L0.graph_exec); L0.graph_exec = nullptr; }
+    if (L0.graph) { cudaGraphDestroy(L0.graph); L0.graph = nullptr; }
+    L0.stream = stream ? (cudaStream_t)stream : L0.own_stream;
     return TOB_OK;
 }
 
@@ -616,33 +677,33 @@ int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_op
     int rc = ensure_device(p->device);
     if (rc != TOB_OK) return rc;
     int launches = 0;
-    p->h_state->next_slice = slice;
-    p->h_state->stride = 1;
-    p->h_state->acc = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(p->d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, p->stream));
+    Lane& L0 = p->lane[0];
+    p->h_state[0].next_slice = slice;
+    p->h_state[0].stride = 1;
+    p->h_state[0].slot = 0;
+    p->h_state[0].slot_stride = 1;
+    CUDA_TRY(cudaMemcpyAsync(L0.d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, L0.stream));
     std::vector<cudaEvent_t> ev(n_ops + 1);
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     int64_t i = 0;
     for (const Op& op : p->prog.invariant_ops) {
-        CUDA_TRY(cudaEventRecord(ev[i], p->stream));
-        CUDA_TRY(launch_op(p, op, &launches));
+        CUDA_TRY(cudaEventRecord(ev[i], L0.stream));
+        CUDA_TRY(launch_op(p, L0, op, &launches));
         i++;
     }
-    if (p->has_terms) {
-        SliceTables t{p->d_term_start, p->d_id_bit, p->d_addr_bit, p->d_leaf_off, (int32_t)p->prog.leaves.size()};
-        CUDA_TRY(launch_begin_slice(p->d_state, t, p->stream));
-    }
+    CUDA_TRY(launch_begin(p, L0, &launches));
     for (const Op& op : p->prog.slice_ops) {
-        CUDA_TRY(cudaEventRecord(ev[i], p->stream));
-        CUDA_TRY(launch_op(p, op, &launches));
+        CUDA_TRY(cudaEventRecord(ev[i], L0.stream));
+        CUDA_TRY(launch_op(p, L0, op, &launches));
         i++;
     }
-    CUDA_TRY(cudaEventRecord(ev[i], p->stream));
-    CUDA_TRY(cudaMemcpyAsync(p->h_state, p->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaEventRecord(ev[i], L0.stream));
+    CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, 1, 0.0, 0, L0.stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_acc, sizeof(double), cudaMemcpyDeviceToHost, L0.stream));
+    CUDA_TRY(cudaStreamSynchronize(L0.stream));
     for (int64_t j = 0; j < n_ops; j++) CUDA_TRY(cudaEventElapsedTime(&ms_per_op[j], ev[j], ev[j + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
-    if (result) *result = p->h_state->acc;
+    if (result) *result = *p->h_readback;
     return TOB_OK;
 }
 

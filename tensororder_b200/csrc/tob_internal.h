@@ -23,7 +23,7 @@ enum OpKind : int32_t {
 };
 
 struct OperandRef {
-    int32_t space = 0;       // 0: leaf region, 1: arena
+    int32_t space = 0;       // 0: leaf region, 1: the running lane's arena, 2: lane 0's arena (slice-invariant tensor)
     int64_t offset = 0;      // doubles from the start of that region
     int32_t leaf = -1;       // leaf-table index when space == 0 (slice offset lookup), else -1
     int32_t node = -1;       // post-order position of the producing node
@@ -87,6 +87,7 @@ struct Program {
     int64_t leaf_doubles = 0;         // device leaf region
     int64_t arena_doubles = 0;        // intermediates
     int64_t ws_doubles = 0;           // split-K workspace
+    int32_t lanes = 1;                // slices in flight at once (each lane has its own arena + workspace)
     int64_t src_leaf_len = 0;
     double total_flops = 0, total_bytes = 0;
     OperandRef root;                  // rank-0 result of one slice

@@ -643,9 +643,21 @@ __global__ void k_begin_slice(DevState* st, SliceTables t) {
     if (threadIdx.x == 0) st->next_slice = sid + st->stride;
 }
 
-__global__ void k_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf) {
+// the rank-0 result of the lane's current slice goes to its slot of the result buffer; the slices of a
+// run may execute on several lanes concurrently, the SUM is taken afterwards in slice order
+__global__ void k_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results) {
     const double* r = operand_base(root, leaf_off, root_leaf);
-    st->acc += r[0];
+    const unsigned long long slot = st->slot;
+    results[slot] = r[0];
+    st->slot = slot + st->slot_stride;
+}
+
+// acc = (previous acc | initial) + results[0] + results[1] + ...   sequentially, exactly like the
+// reference's `result += tensor_result[()]` loop (base_api.py:25-27)
+__global__ void k_final_sum(double* acc, const double* results, int count, double initial, int use_previous) {
+    double s = use_previous ? acc[0] : initial;
+    for (int i = 0; i < count; i++) s += results[i];
+    acc[0] = s;
 }
 
 cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream) {
@@ -653,8 +665,15 @@ cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, cudaStream_t stream) {
-    k_accum<<<1, 1, 0, stream>>>(st, root, leaf_off, root_leaf);
+cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results,
+                         cudaStream_t stream) {
+    k_accum<<<1, 1, 0, stream>>>(st, root, leaf_off, root_leaf, results);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous,
+                             cudaStream_t stream) {
+    k_final_sum<<<1, 1, 0, stream>>>(acc, results, count, initial, use_previous);
     return cudaGetLastError();
 }
 
@@ -665,12 +684,15 @@ cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf
 // kernel launches per slice by one.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
-                                                   const double* leaves, double* arena, const long long* leaf_off) {
+                                                   const double* leaves, double* arena, const double* arena0,
+                                                   const long long* leaf_off) {
     const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
     for (int i = first; i < last; i++) {
         const MicroOpDev op = ops[i];
-        const double* A = (op.a_space ? arena : leaves) + op.a_off + (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
-        const double* B = (op.b_space ? arena : leaves) + op.b_off + (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
+        const double* A = (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
+                          (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
+        const double* B = (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
+                          (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
         double* C = arena + op.c_off;
         const int tot = op.m + op.n, k = op.k;
         const unsigned outs = 1u << tot;
@@ -706,8 +728,8 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
 }
 
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
-                             double* arena, const long long* leaf_off, cudaStream_t stream) {
-    k_microtree<<<n_ctas, 256, 0, stream>>>(ops, cta_start, leaves, arena, leaf_off);
+                             double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream) {
+    k_microtree<<<n_ctas, 256, 0, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off);
     return cudaGetLastError();
 }
 

@@ -34,15 +34,15 @@ struct MicroOpDev {
     long long a_off, b_off, c_off;  // doubles: a/b inside their space, c inside the arena
     int32_t a_leaf, b_leaf;         // leaf_off index or -1
     uint16_t mask_m;
-    uint8_t a_space, b_space;       // 0 leaves, 1 arena
+    uint8_t a_space, b_space;       // 0 leaves, 1 this lane's arena, 2 lane 0's arena (slice-invariant tensor)
     uint8_t m, n, k, pad;
 };
 
-struct DevState {
-    unsigned long long next_slice;
+struct DevState {                  // one per lane
+    unsigned long long next_slice;  // slice id the lane's next slice uses
     unsigned long long stride;
-    double acc;
-    double pad;
+    unsigned long long slot;        // index into the per-slice result buffer for the lane's current slice
+    unsigned long long slot_stride;
 };
 
 struct SliceTables {            // device pointers
@@ -68,8 +68,11 @@ struct PermuteParams {
 
 cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
-                             double* arena, const long long* leaf_off, cudaStream_t stream);
-cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, cudaStream_t stream);
+                             double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream);
+cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results,
+                         cudaStream_t stream);
+cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous,
+                             cudaStream_t stream);
 cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream);
 cudaError_t launch_permute(const double* in, double* out, int rank, const int32_t* src_bit, cudaStream_t stream);
 cudaError_t configure_kernels();

@@ -113,45 +113,55 @@ def flatten_plan(plan, tensor_factory=None) -> FlatPlan:
     built_at = {}  # tensor index -> offset (a tensor named by two leaves is stored once)
     total = 0
     stack: List[int] = []
+    # hot loop (one iteration per tree node): bind everything to locals
+    index_list = network.index_list
+    factory, commit = arena.factory, arena.commit
+    nl_append, nr_append, nf_append = node_left.append, node_right.append, node_leaf.append
+    push, pop = stack.append, stack.pop
+    pos = 0
+    n_leaves = 0
     for node in plan.tree.iterate_postorder():
-        pos = len(node_left)
         if node.is_leaf:
-            t = int(node.tensor_index)
-            edges = [int(e) for e in network.index_list(t)]
-            if edges and min(edges) < 0:
+            t = node.tensor_index
+            edges = index_list(t)
+            rank = len(edges)
+            if rank and min(edges) < 0:
                 raise ValueError("tensor %d has a dangling index; the network cannot contract to a scalar" % t)
-            if t not in built_at:
-                size = 1 << len(edges)
+            off = built_at.get(t)
+            if off is None:
+                size = 1 << rank
                 if tensor_factory is None:
-                    built = network[t].build(arena.factory)
+                    built = network[t].build(factory)
                     if getattr(built, "size", size) != size:
                         raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
-                    built_at[t] = arena.commit(built, size)
+                    off = commit(built, size)
                 else:
                     data = np.ascontiguousarray(network[t].build(tensor_factory), dtype=np.float64)
                     if data.size != size:
                         raise ValueError("tensor %d: only indices of extent 2 are supported" % t)
-                    built_at[t] = total
+                    off = total
                     chunks.append(data.reshape(-1))
                     total += data.size
-            node_left.append(-1)
-            node_right.append(-1)
-            node_leaf.append(len(leaf_rank))
-            leaf_rank.append(len(edges))
-            leaf_off.append(built_at[t])
+                built_at[t] = off
+            nl_append(-1)
+            nr_append(-1)
+            nf_append(n_leaves)
+            n_leaves += 1
+            leaf_rank.append(rank)
+            leaf_off.append(off)
             if group_of:
-                axis_edge.extend(-(group_of[e] + 1) if e in group_of else e for e in edges)
+                axis_edge.extend([-(group_of[e] + 1) if e in group_of else e for e in edges])
             else:
                 axis_edge.extend(edges)
             axis_start.append(len(axis_edge))
             leaf_tensor_index.append(t)
         else:
-            right = stack.pop()
-            left = stack.pop()
-            node_left.append(left)
-            node_right.append(right)
-            node_leaf.append(-1)
-        stack.append(pos)
+            right = pop()
+            nl_append(pop())
+            nr_append(right)
+            nf_append(-1)
+        push(pos)
+        pos += 1
     if len(stack) != 1:
         raise ValueError("contraction tree is not a single rooted tree")
     if tensor_factory is None:

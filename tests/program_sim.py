@@ -54,6 +54,8 @@ def run_program(desc, flat, first=0, count=None, stride=1):
         if ref["space"] == 0:
             off = ref["offset"] + (leaf_off[ref["leaf"]] if ref["leaf"] >= 0 else 0)
             return leaves[off: off + size]
+        if ref["space"] == 2:  # slice-invariant tensor: lane 0's arena (the simulator has one arena)
+            assert ref["node"] in invariant_nodes, "space 2 must name a hoisted result"
         return arena[ref["offset"]: ref["offset"] + size]
 
     def do(op):
@@ -79,6 +81,11 @@ def run_program(desc, flat, first=0, count=None, stride=1):
         out[addr.reshape(-1)] = Cm.reshape(-1)
 
     acc = 0.0
+    invariant_nodes = set()
+    for op in desc["invariant_ops"]:
+        invariant_nodes.add(op.get("node"))
+        for sub in op.get("micro", []):
+            invariant_nodes.add(sub["node"])
     for op in desc["invariant_ops"]:
         do(op)
     sid = first

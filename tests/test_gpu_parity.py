@@ -160,6 +160,30 @@ def test_interruptible_run_is_bit_identical_and_honours_sigalrm():
     assert time.time() - t0 < 1.5  # interrupted after a chunk, not after all 64 slices
 
 
+@pytest.mark.parametrize("name,variant", [("vc100_lineflow", "min4"), ("vc150_lineflow", "min4"), ("vc50_mcc_lineflow", "min3"),
+                                          ("vc200_lineflow", "min3")])
+def test_two_slice_lanes_give_the_sequential_sum(name, variant):
+    """Slices run two at a time on separate streams/arenas; per-slice results are summed afterwards in
+    slice order, so the count is bit-identical to the one-lane run (and to the reference's loop order)."""
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name).variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    one = CompiledPlan(flat, slice_lanes=1)
+    two = CompiledPlan(flat, slice_lanes=2)
+    assert one.describe()["lanes"] == 1 and two.describe()["lanes"] == 2
+    one.upload()
+    two.upload()
+    a, b = one.run(), two.run()
+    assert float(a).hex() == float(b).hex()
+    _check(b, pp.expected)
+    assert float(two.run()).hex() == float(a).hex()  # second run: graph replay on both lanes
+    assert float(two.run(first=1, count=5, stride=1)).hex() == float(one.run(first=1, count=5, stride=1)).hex()
+    one.close()
+    two.close()
+
+
 def test_contract_single_network_entry():
     pp = load_golden("vc50_factorflow")
     plan = pp.as_execution_plan()
