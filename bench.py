@@ -236,6 +236,7 @@ def b200_arm(args, rank, world, local_rank):
         cp = CompiledPlan(flatten_plan(it["pp"].as_execution_plan()), device=local_rank)
         cp.upload()
         cp.set_stream(stream.cuda_stream)
+        cp.set_gemm_timing(True)  # CUDA-event pair around every DMMA GEMM of the timed steps (roofline)
         it["cp"] = cp
     counts = torch.zeros(n_inst, dtype=torch.float64, device=dev)
     step_ms, launches = [], 0
@@ -381,6 +382,7 @@ def b200_arm(args, rank, world, local_rank):
                 pp = PortablePlan.load(os.path.join(GOLDEN, "vc%d_lineflow.json.gz" % n))
                 cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), device=local_rank)
                 cp.upload()
+                cp.set_gemm_timing(True)
                 cp.run()
                 c = cp.run()
                 g = cp.last_gemm

@@ -116,9 +116,12 @@ double tob_plan_last_ms(const tob_plan* plan);
 /* Number of kernels launched by the last tob_plan_run. */
 int64_t tob_plan_last_launches(const tob_plan* plan);
 
-/* DMMA GEMM launches of the last tob_plan_run when it ran as plain stream launches: summed CUDA-event
- * duration, algorithmic flops (2*2^(fL+fR+k) per join) and launch count.  All zero
- * when the run was replayed as a graph. */
+/* Per-kernel timing of the DMMA GEMM launches (off by default).  When on, every GEMM of a stream-mode run
+ * is bracketed by a CUDA-event pair and GEMMs of the two slice lanes are chained so each pair brackets
+ * one GEMM (costs ~3 % on mid-size sliced plans, where overlapping GEMM tails otherwise helps).
+ * tob_plan_last_gemm: summed event duration, algorithmic flops (2*2^(fL+fR+k) per join)
+ * and launch count of the last run; all zero when timing is off or the run was replayed as a graph. */
+int tob_plan_set_gemm_timing(tob_plan* plan, int32_t on);
 int tob_plan_last_gemm(const tob_plan* plan, double* ms, double* flops, int64_t* launches);
 
 /* Run on a caller-owned CUDA stream (cudaStream_t) instead of the plan's own; call after

@@ -157,6 +157,9 @@ class CompiledPlan:
         cabi.lib.tob_plan_last_gemm(self._handle, byref(ms), byref(fl), byref(n))
         return ms.value, fl.value, n.value
 
+    def set_gemm_timing(self, on: bool = True) -> None:
+        cabi.lib.tob_plan_set_gemm_timing(self._handle, 1 if on else 0)
+
     def set_stream(self, cuda_stream_handle: int) -> None:
         rc = cabi.lib.tob_plan_set_stream(self._handle, c_void_p(cuda_stream_handle))
         if rc != cabi.TOB_OK:

@@ -73,6 +73,7 @@ struct tob_plan {
     double last_gemm_ms = 0, last_gemm_flops = 0;
     int64_t last_gemm_launches = 0;
     double slice_flops = 0;
+    bool time_gemm = false;
 };
 
 static bool g_configured[64] = {false};  // per device: kernel attributes live in the device's context
@@ -547,9 +548,14 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     const bool as_graph = (ug == 1) || (ug == 2 && p->slice_flops < 2e9 && (p->runs > 0 || count >= 4));
     const bool skip_invariant = (flags & TOB_RUN_SKIP_INVARIANT) != 0 && p->runs > 0;
     size_t n_gemm = 0;
-    // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py)
+    cudaEvent_t last_gemm_end = nullptr;
+    const Lane* last_gemm_lane = nullptr;
+    // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py).
+    // GEMMs of different lanes are chained (a GEMM waits for the previous GEMM of the other lane): two
+    // tensor-pipe-bound kernels gain nothing from sharing the SMs, and each event pair then brackets one
+    // GEMM running alone with only the other lane's small kernels beside it.
     auto timed_op = [&](const Lane& L, const Op& op) -> int {
-        if (op.kind != OP_GEMM || as_graph) {
+        if (op.kind != OP_GEMM || as_graph || !p->time_gemm) {
             CUDA_TRY(launch_op(p, L, op, &launches));
             return TOB_OK;
         }
@@ -561,9 +567,12 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
             p->gemm_events.push_back(b);
             p->gemm_event_flops.push_back(0.0);
         }
+        if (last_gemm_end && last_gemm_lane != &L) CUDA_TRY(cudaStreamWaitEvent(L.stream, last_gemm_end, 0));
         CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm], L.stream));
         CUDA_TRY(launch_op(p, L, op, &launches));
         CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm + 1], L.stream));
+        last_gemm_end = p->gemm_events[2 * n_gemm + 1];
+        last_gemm_lane = &L;
         p->gemm_event_flops[n_gemm] = op.flops;
         n_gemm++;
         return TOB_OK;
@@ -646,6 +655,12 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     p->last_gemm_launches = (int64_t)n_gemm;
     *result = *p->h_readback;
     p->runs++;
+    return TOB_OK;
+}
+
+int tob_plan_set_gemm_timing(tob_plan* p, int32_t on) {
+    if (!p) { set_error("NULL argument"); return TOB_E_INVALID; }
+    p->time_gemm = on != 0;
     return TOB_OK;
 }
 
