@@ -439,8 +439,8 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
 // SWZ: dense 128-byte rows with the 16-byte chunk index XOR-ed by ((row & 3) << 1) instead of the padded
 // 160-byte rows: the 8x4 fragment loads stay conflict-free and a stage shrinks from 30 KB to 24 KB, so FOUR
 // stages fit twice per SM (ncu showed consumers waiting on `full` 24 % of the time with three).
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK, bool SWZ>
-__global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParams p) {
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK, bool SWZ, int NPROD = 1>
+__global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_ws(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NC = WM * WN * 32;  // consumer threads
     constexpr int TK = 16, LDS = SWZ ? TK : TK + 4, K4 = TK / 4;
@@ -473,19 +473,23 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], BULK ? 1 : 32);  // bulk: the producer's expect_tx arrive + STAGE_BYTES of transactions
+            mbar_init(&full[s], BULK ? 1 : 32 * NPROD);  // bulk: the producer's expect_tx arrive + STAGE_BYTES of transactions
             mbar_init(&empty[s], WM * WN);      // one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int i = tid; i < TM; i += NC + 32) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
-    for (int i = tid; i < TN; i += NC + 32) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+    for (int i = tid; i < TM; i += NC + 32 * NPROD) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NC + 32 * NPROD) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
     __syncthreads();
 
-    if (warp == WM * WN) {
+    if (warp >= WM * WN) {
+        const int pw = warp - WM * WN;  // producer warp index: takes every NPROD-th group of 4 rows
         // ===================== producer warp =====================
         const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
         const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
+        // this lane's first source element of A / B (row = (lane >> 3) + 4 * pw, 16-byte chunk = lane & 7)
+        const double* a_lane = A + ((unsigned long long)((lane >> 3) + 4 * pw) << k) + (lane & 7) * 2;
+        const double* b_lane = B + ((unsigned long long)((lane >> 3) + 4 * pw) << k) + (lane & 7) * 2;
         for (int kt = 0; kt < KT; kt++) {
             const int s = kt % STAGES;
             if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);  // consumers released this slot
@@ -508,14 +512,16 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32, MINB) k_gemm_dmma_ws(KParam
                 // LDGSTS from the producer warp only; the stage's "full" barrier (count 32) completes when
                 // every lane's copies have landed (cp.async.mbarrier.arrive.noinc)
                 const int chunk = lane & 7, r0 = lane >> 3;  // r0 = row & 3 for every row this lane copies
-                const double* ag = A + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
-                const double* bg = B + ((unsigned long long)r0 << k) + kt * TK + chunk * 2;
-                const unsigned long long step = 4ull << k;
                 const int dchunk = SWZ ? (chunk ^ (r0 << 1)) : chunk;
-#pragma unroll 8
-                for (int i = 0; i < TM / 4; i++) cp_async16(as + (r0 + 4 * i) * LDS + dchunk * 2, ag + i * step);
-#pragma unroll 8
-                for (int i = 0; i < TN / 4; i++) cp_async16(bs + (r0 + 4 * i) * LDS + dchunk * 2, bg + i * step);
+                const unsigned long long step = (4ull * NPROD) << k;  // global stride between this warp's row groups
+                const double* ag = a_lane + kt * TK;
+                const double* bg = b_lane + kt * TK;
+                double* ad = as + (r0 + 4 * pw) * LDS + dchunk * 2;
+                double* bd = bs + (r0 + 4 * pw) * LDS + dchunk * 2;
+#pragma unroll
+                for (int i = 0; i < TM / 4 / NPROD; i++) cp_async16(ad + i * (4 * NPROD * LDS), ag + i * step);
+#pragma unroll
+                for (int i = 0; i < TN / 4 / NPROD; i++) cp_async16(bd + i * (4 * NPROD * LDS), bg + i * step);
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&full[s]))
                              : "memory");
             }
@@ -605,6 +611,8 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true, false>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true>
+#define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
+#define GEMM_76_WZ4 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 4>
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -623,6 +631,10 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WZ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WZ4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     return e;
 }
 
@@ -760,13 +772,20 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             else
                 GEMM_77_A<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 16, 4>(), stream>>>(p);
         } else if (op.tm_log2 == 7 && op.tn_log2 == 6) {
-            // TOB_GEMM_WS: 2 (default) = warp-specialised pipeline, producer warp issuing LDGSTS, mbarrier
-            // full/empty stages (measured +0.4 % at K=65536, +3 % at K=1024, +14 % at K=64 over the
-            // CTA-barrier pipeline); 1 = same with 128-byte bulk copies (UBLKCP: 2.4x SLOWER, the copy engine
-            // is request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
-            static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 2;
+            // TOB_GEMM_WS: 4 (default) = warp-specialised pipeline, TWO producer warps issuing LDGSTS into a
+            // swizzled 4-stage ring, mbarrier full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
+            // (the producer's issue rate was the limiter: one producer warp gives 33.8-34.1, four spill);
+            // 2/3 = one producer warp (padded 3-stage / swizzled 4-stage ring); 1 = 128-byte bulk copies
+            // (UBLKCP: 2.4x SLOWER, request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
+            static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 4;
             if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
                 GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
+            else if (ws == 4 && (op.k - op.ksplit_log2) >= 8)
+                GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
+            else if (ws == 4 && (op.k - op.ksplit_log2) >= 6)  // K = 64, 128: the shorter 3-stage ring fills faster
+                GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
+            else if (ws == 5 && (op.k - op.ksplit_log2) >= 6)
+                GEMM_76_WZ4<<<(unsigned)blocks, 384, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
             else if ((ws == 3 || (ws == 2 && (op.k - op.ksplit_log2) >= 8)) && (op.k - op.ksplit_log2) >= 6)
                 // swizzled dense rows, 4 stages: +0.2 % (K=65536) .. +1.5 % (K=1024) over the padded 3-stage ring
                 GEMM_76_WZ<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
