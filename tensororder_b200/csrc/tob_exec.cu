@@ -501,7 +501,11 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
     if (op.kind == OP_MICRO) {
         const int w = op.micro_which;
         (*launches)++;
-        return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)p->prog.micro[w].cta_start.size() - 1,
+        const MicroProgram& mp = p->prog.micro[w];
+        int max_ops = 1;
+        for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
+        const int smem_ops = std::min(max_ops, (int)(40 * 1024 / sizeof(MicroOpDev)));
+        return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops,
                                 p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, L.stream);
     }
     KParams k = make_params(p, L, op);

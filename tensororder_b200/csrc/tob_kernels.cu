@@ -697,10 +697,22 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
                                                    const double* leaves, double* arena, const double* arena0,
-                                                   const long long* leaf_off) {
+                                                   const long long* leaf_off, int smem_ops) {
+    extern __shared__ __align__(16) unsigned char micro_smem[];
+    MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
     const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
+    // stage this CTA's join descriptors in shared memory once: the serial chain of joins then pays one
+    // L2 round trip per join (its operands) instead of two (descriptor, then operands)
+    const bool staged = (last - first) <= smem_ops;
+    if (staged) {
+        const int4* src = reinterpret_cast<const int4*>(ops + first);
+        int4* dst = reinterpret_cast<int4*>(sops);
+        const int n16 = (last - first) * (int)(sizeof(MicroOpDev) / 16);
+        for (int i = threadIdx.x; i < n16; i += 256) dst[i] = src[i];
+        __syncthreads();
+    }
     for (int i = first; i < last; i++) {
-        const MicroOpDev op = ops[i];
+        const MicroOpDev op = staged ? sops[i - first] : ops[i];
         const double* A = (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
                           (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
         const double* B = (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
@@ -720,14 +732,14 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
             const double* br = B + ((size_t)ni << k);
             double s;
             if (k == 0) {
-                s = ar[0] * br[0];
+                s = __ldcg(ar) * __ldcg(br);
             } else {
                 const double2* a2 = reinterpret_cast<const double2*>(ar);
                 const double2* b2 = reinterpret_cast<const double2*>(br);
                 const int K2 = 1 << (k - 1);
                 double s0 = 0.0, s1 = 0.0;
                 for (int j = 0; j < K2; j++) {
-                    const double2 x = a2[j], y = b2[j];
+                    const double2 x = __ldcg(a2 + j), y = __ldcg(b2 + j);
                     s0 = fma(x.x, y.x, s0);
                     s1 = fma(x.y, y.y, s1);
                 }
@@ -739,9 +751,9 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
     }
 }
 
-cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream) {
-    k_microtree<<<n_ctas, 256, 0, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off);
+    k_microtree<<<n_ctas, 256, (size_t)smem_ops * sizeof(MicroOpDev), stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops);
     return cudaGetLastError();
 }
 

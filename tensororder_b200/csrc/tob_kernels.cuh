@@ -36,7 +36,9 @@ struct MicroOpDev {
     uint16_t mask_m;
     uint8_t a_space, b_space;       // 0 leaves, 1 this lane's arena, 2 lane 0's arena (slice-invariant tensor)
     uint8_t m, n, k, pad;
+    uint64_t pad2;                  // 48 bytes: descriptors are staged into shared memory with 16-byte copies
 };
+static_assert(sizeof(MicroOpDev) % 16 == 0, "MicroOpDev is staged with 16-byte copies");
 
 struct DevState {                  // one per lane
     unsigned long long next_slice;  // slice id the lane's next slice uses
@@ -67,7 +69,7 @@ struct PermuteParams {
 };
 
 cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
-cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, const double* leaves,
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream);
 cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results,
                          cudaStream_t stream);
