@@ -440,6 +440,27 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
             m.m = (uint8_t)op.m; m.n = (uint8_t)op.n; m.k = (uint8_t)op.k;
             mo[j] = m;
         }
+        // per CTA: forward each result to the next join when that join consumes it, stage small leaf
+        // operands in the CTA's shared leaf cache
+        for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) {
+            int cache_used = 0;
+            for (int j = mp.cta_start[c]; j < mp.cta_start[c + 1]; j++) {
+                const Op& op = mp.ops[j];
+                if (j > mp.cta_start[c]) {
+                    const Op& prev = mp.ops[j - 1];
+                    const bool small = ((int64_t)1 << (prev.m + prev.n)) <= kMicroFwdMax;
+                    if (small && op.a.space != 0 && op.a.node == prev.node) { mo[j].a_src = 1; mo[j - 1].fwd_out = 1; }
+                    if (small && op.b.space != 0 && op.b.node == prev.node) { mo[j].b_src = 1; mo[j - 1].fwd_out = 1; }
+                }
+                const int a_sz = 1 << (op.m + op.k), b_sz = 1 << (op.n + op.k);
+                if (op.a.space == 0 && a_sz <= kMicroStageMax && cache_used + a_sz <= kMicroLeafCache) {
+                    mo[j].a_src = 2; mo[j].a_soff = (uint16_t)cache_used; cache_used += std::max(a_sz, 2);
+                }
+                if (op.b.space == 0 && b_sz <= kMicroStageMax && cache_used + b_sz <= kMicroLeafCache) {
+                    mo[j].b_src = 2; mo[j].b_soff = (uint16_t)cache_used; cache_used += std::max(b_sz, 2);
+                }
+            }
+        }
         if (!mp.cta_start.empty()) memcpy(h + o_mstart[w], mp.cta_start.data(), mp.cta_start.size() * sizeof(int32_t));
     }
     double* h_leaves = reinterpret_cast<double*>(h + o_leaves);
@@ -504,7 +525,7 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
         const MicroProgram& mp = p->prog.micro[w];
         int max_ops = 1;
         for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
-        const int smem_ops = std::min(max_ops, (int)(40 * 1024 / sizeof(MicroOpDev)));
+        const int smem_ops = std::min(max_ops, (int)(64 * 1024 / sizeof(MicroOpDev)));
         return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops,
                                 p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, L.stream);
     }

@@ -614,6 +614,9 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 #define GEMM_76_WZ4 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 4>
 
+__global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
+                            double* arena, const double* arena0, const long long* leaf_off, int smem_ops);
+
 cudaError_t configure_kernels() {
     cudaError_t e;
     e = cudaFuncSetAttribute(GEMM_77_A, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 16, 4>());
@@ -635,6 +638,9 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_WZ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_microtree, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
     return e;
 }
 
@@ -695,14 +701,33 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 // so a __syncthreads between joins is the only synchronisation.  Replaces hundreds of launch-bound
 // kernel launches per slice by one.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double micro_dot(const double* ar, const double* br, int k, bool a_glob, bool b_glob) {
+    if (k == 0) return (a_glob ? __ldcg(ar) : ar[0]) * (b_glob ? __ldcg(br) : br[0]);
+    const double2* a2 = reinterpret_cast<const double2*>(ar);
+    const double2* b2 = reinterpret_cast<const double2*>(br);
+    const int K2 = 1 << (k - 1);
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = 0; j < K2; j++) {
+        const double2 x = a_glob ? __ldcg(a2 + j) : a2[j];
+        const double2 y = b_glob ? __ldcg(b2 + j) : b2[j];
+        s0 = fma(x.x, y.x, s0);
+        s1 = fma(x.y, y.y, s1);
+    }
+    return s0 + s1;
+}
+
+// Shared memory: [join descriptors | leaf cache | two forward buffers].  The serial chain of joins a CTA
+// walks is latency-bound: with the descriptors and the (tiny) leaf operands staged up front and each
+// result handed to the next join through the forward buffer, the critical path of a join is shared-memory
+// latency instead of two L2 round trips (store result, load it back).
 __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
                                                    const double* leaves, double* arena, const double* arena0,
                                                    const long long* leaf_off, int smem_ops) {
     extern __shared__ __align__(16) unsigned char micro_smem[];
     MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
+    double* cache = reinterpret_cast<double*>(micro_smem + (size_t)smem_ops * sizeof(MicroOpDev));
+    double* fwd = cache + kMicroLeafCache;  // [2][kMicroFwdMax]
     const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
-    // stage this CTA's join descriptors in shared memory once: the serial chain of joins then pays one
-    // L2 round trip per join (its operands) instead of two (descriptor, then operands)
     const bool staged = (last - first) <= smem_ops;
     if (staged) {
         const int4* src = reinterpret_cast<const int4*>(ops + first);
@@ -710,17 +735,35 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
         const int n16 = (last - first) * (int)(sizeof(MicroOpDev) / 16);
         for (int i = threadIdx.x; i < n16; i += 256) dst[i] = src[i];
         __syncthreads();
+        // leaf operands: one thread per (join, operand), a handful of doubles each
+        for (int i = threadIdx.x; i < 2 * (last - first); i += 256) {
+            const MicroOpDev& op = sops[i >> 1];
+            const bool is_b = i & 1;
+            if ((is_b ? op.b_src : op.a_src) != 2) continue;
+            const int leaf = is_b ? op.b_leaf : op.a_leaf;
+            const double* g = leaves + (is_b ? op.b_off : op.a_off) + (leaf >= 0 ? leaf_off[leaf] : 0);
+            double* d = cache + (is_b ? op.b_soff : op.a_soff);
+            const int n = 1 << ((is_b ? op.n : op.m) + op.k);
+            for (int e = 0; e < n; e++) d[e] = __ldcg(g + e);
+        }
+        __syncthreads();
     }
     for (int i = first; i < last; i++) {
         const MicroOpDev op = staged ? sops[i - first] : ops[i];
-        const double* A = (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
-                          (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
-        const double* B = (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
-                          (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
+        const int a_src = staged ? op.a_src : 0, b_src = staged ? op.b_src : 0;
+        const double* prev = fwd + ((i - first + 1) & 1) * kMicroFwdMax;  // written by join i-1
+        double* mine = fwd + ((i - first) & 1) * kMicroFwdMax;
+        const double* A = a_src == 1 ? prev : a_src == 2 ? cache + op.a_soff
+                          : (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
+                                (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
+        const double* B = b_src == 1 ? prev : b_src == 2 ? cache + op.b_soff
+                          : (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
+                                (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
         double* C = arena + op.c_off;
         const int tot = op.m + op.n, k = op.k;
         const unsigned outs = 1u << tot;
         const unsigned mask = op.mask_m;
+        const bool fwd_out = staged && op.fwd_out;
         for (unsigned c = threadIdx.x; c < outs; c += 256) {
             unsigned mi = 0, ni = 0, im = 0, in = 0;
             for (int b = 0; b < tot; b++) {
@@ -728,24 +771,9 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
                 if ((mask >> b) & 1u) { mi |= bit << im; im++; }
                 else { ni |= bit << in; in++; }
             }
-            const double* ar = A + ((size_t)mi << k);
-            const double* br = B + ((size_t)ni << k);
-            double s;
-            if (k == 0) {
-                s = __ldcg(ar) * __ldcg(br);
-            } else {
-                const double2* a2 = reinterpret_cast<const double2*>(ar);
-                const double2* b2 = reinterpret_cast<const double2*>(br);
-                const int K2 = 1 << (k - 1);
-                double s0 = 0.0, s1 = 0.0;
-                for (int j = 0; j < K2; j++) {
-                    const double2 x = __ldcg(a2 + j), y = __ldcg(b2 + j);
-                    s0 = fma(x.x, y.x, s0);
-                    s1 = fma(x.y, y.y, s1);
-                }
-                s = s0 + s1;
-            }
+            const double s = micro_dot(A + ((size_t)mi << k), B + ((size_t)ni << k), k, a_src == 0, b_src == 0);
             C[c] = s;
+            if (fwd_out) mine[c] = s;
         }
         __syncthreads();
     }
@@ -753,7 +781,8 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
 
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream) {
-    k_microtree<<<n_ctas, 256, (size_t)smem_ops * sizeof(MicroOpDev), stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops);
+    const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double);
+    k_microtree<<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops);
     return cudaGetLastError();
 }
 

@@ -35,9 +35,17 @@ struct MicroOpDev {
     int32_t a_leaf, b_leaf;         // leaf_off index or -1
     uint16_t mask_m;
     uint8_t a_space, b_space;       // 0 leaves, 1 this lane's arena, 2 lane 0's arena (slice-invariant tensor)
-    uint8_t m, n, k, pad;
-    uint64_t pad2;                  // 48 bytes: descriptors are staged into shared memory with 16-byte copies
+    uint8_t m, n, k;
+    uint8_t fwd_out;                // 1: the next join of this CTA reads this result from the shared forward buffer
+    // operand source inside k_microtree: 0 global memory, 1 the previous join's result (shared forward
+    // buffer), 2 leaf staged into the CTA's shared leaf cache at a_soff / b_soff (doubles)
+    uint8_t a_src, b_src;
+    uint16_t a_soff, b_soff;
+    uint16_t pad2;                  // 48 bytes: descriptors are staged into shared memory with 16-byte copies
 };
+constexpr int kMicroLeafCache = 2048;   // doubles of staged leaves per CTA
+constexpr int kMicroFwdMax = 2048;      // largest result (doubles) forwarded through shared memory
+constexpr int kMicroStageMax = 64;      // largest leaf operand (doubles) staged
 static_assert(sizeof(MicroOpDev) % 16 == 0, "MicroOpDev is staged with 16-byte copies");
 
 struct DevState {                  // one per lane
