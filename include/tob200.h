@@ -116,6 +116,13 @@ double tob_plan_last_ms(const tob_plan* plan);
 /* Number of kernels launched by the last tob_plan_run. */
 int64_t tob_plan_last_launches(const tob_plan* plan);
 
+/* Exact mode (the reference's `--entry_type=bigint`, numpy_apis.py:15-22): with a prime modulus p < 2^23
+ * every kernel reduces its sums modulo p (tensors hold residues as doubles; sums of <= 128 products stay
+ * below 2^53, so all arithmetic is exact, on the same DMMA path).  The leaves passed to tob_plan_upload
+ * must already be residues in [0, p).  The host combines the residues of several primes by CRT.
+ * modulus = 0 restores float64 arithmetic. */
+int tob_plan_set_modulus(tob_plan* plan, double modulus);
+
 /* Per-kernel timing of the DMMA GEMM launches (off by default).  When on, every GEMM of a stream-mode run
  * is bracketed by a CUDA-event pair and GEMMs of the two slice lanes are chained so each pair brackets
  * one GEMM (costs ~3 % on mid-size sliced plans, where overlapping GEMM tails otherwise helps).

@@ -39,6 +39,30 @@ def _ptr(arr: np.ndarray, ctype):
     return arr.ctypes.data_as(ctypes.POINTER(ctype))
 
 
+def _primes_below(limit: int, count: int):
+    """The `count` largest primes below `limit` (trial division; limit is 2^23, so divisors < 2897)."""
+    out = []
+    n = limit - 1
+    while len(out) < count:
+        if n % 2 and all(n % d for d in range(3, int(n ** 0.5) + 1, 2)):
+            out.append(n)
+        n -= 1
+    return out
+
+
+EXACT_PRIMES = _primes_below(1 << 23, 96)  # ~23 bits each: enough for counts up to 2^2200
+
+
+def crt(residues, moduli) -> int:
+    """Chinese remainder: the integer in [0, prod(moduli)) with the given residues."""
+    x, m = 0, 1
+    for r, p in zip(residues, moduli):
+        t = ((r - x) * pow(m, -1, p)) % p
+        x += m * t
+        m *= p
+    return x
+
+
 class CompiledPlan:
     """Owns one `tob_plan` (device arena, leaf tensors, CUDA graph)."""
 
@@ -157,6 +181,11 @@ class CompiledPlan:
         cabi.lib.tob_plan_last_gemm(self._handle, byref(ms), byref(fl), byref(n))
         return ms.value, fl.value, n.value
 
+    def set_modulus(self, modulus: int) -> None:
+        rc = cabi.lib.tob_plan_set_modulus(self._handle, float(modulus))
+        if rc != cabi.TOB_OK:
+            raise ValueError("tob_plan_set_modulus: " + cabi.last_error())
+
     def set_gemm_timing(self, on: bool = True) -> None:
         cabi.lib.tob_plan_set_gemm_timing(self._handle, 1 if on else 0)
 
@@ -203,8 +232,10 @@ class B200API:
     # ---- configuration (tensororder.py:205-217, execution.py:82-85) ----
     def add_argument(self, key, value):
         if key == "entry_type":
-            if value != "float64":
-                raise ValueError("Unknown b200 type %s (only float64 is implemented)" % value)
+            # float64: the DMMA path.  bigint: the reference's exact mode (numpy object arrays of Python ints,
+            # numpy_apis.py:21) done as residues modulo ~23-bit primes on the same kernels + CRT on the host.
+            if value not in ("float64", "bigint"):
+                raise ValueError("Unknown b200 type %s (float64 and bigint are implemented)" % value)
             self._entry_type = value
         elif key == "thread_limit":
             pass  # BLAS thread cap of the numpy backend; no host threads are used here
@@ -242,6 +273,8 @@ class B200API:
 
     # ---- the primary entry (base_api.py:17-28, called from execution.py:136) ----
     def contract_sliced(self, execution_plan, num_slice_limit=None):
+        if self._entry_type == "bigint":
+            return self._contract_exact(execution_plan, num_slice_limit)
         t0 = time.perf_counter()
         flat = flatten_plan(execution_plan)  # leaves are built through a buffer-backed create_tensor
         rank, world = self._rank_world()
@@ -269,6 +302,80 @@ class B200API:
         finally:
             compiled.close()
         return np.float64(result)
+
+    # ---- exact counts (entry_type = bigint) ----
+    def _contract_exact(self, execution_plan, num_slice_limit=None):
+        """Exact integer result, any magnitude: one float64 pass sizes the answer, then the same compiled
+        plan runs once per prime p < 2^23 with every kernel reducing modulo p (all sums stay below 2^53, so
+        FP64 arithmetic is exact), and the residues are combined by CRT.  Primes are added until the
+        reconstruction is stable and agrees with the float64 estimate."""
+        import dataclasses
+        import math
+
+        t0 = time.perf_counter()
+        flat = flatten_plan(execution_plan)
+        if not np.all(np.isfinite(flat.leaf_data)) or not np.array_equal(flat.leaf_data, np.rint(flat.leaf_data)) \
+                or np.any(np.abs(flat.leaf_data) >= 2.0 ** 53):
+            raise ValueError("entry_type bigint needs integer-valued tensors (weights must be integers)")
+        rank, world = self._rank_world()
+        compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
+                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
+                                use_microtree=self._microtree, slice_lanes=self._lanes)
+        try:
+            total = compiled.num_slices
+            if num_slice_limit is not None:
+                total = min(total, int(num_slice_limit))
+            count = 0 if rank >= total else (total - rank + world - 1) // world
+            first = rank if count else 0
+
+            def one_pass(leaf_data, modulus):
+                compiled.flat = dataclasses.replace(flat, leaf_data=np.ascontiguousarray(leaf_data))
+                compiled.upload()
+                compiled.set_modulus(modulus)
+                partial = compiled.run_interruptible(first=first, count=count, stride=world)
+                return self._all_reduce(partial) if world > 1 else partial
+
+            estimate = float(one_pass(flat.leaf_data, 0))
+            if math.isfinite(estimate):
+                bits = math.log2(abs(estimate) + 1.0) + 4.0
+            else:  # beyond float64: a-priori bound, the product over tensors of their 1-norms
+                bits = 4.0
+                for l in range(flat.n_leaves):
+                    off = int(flat.leaf_data_offset[l])
+                    bits += math.log2(max(float(np.abs(flat.leaf_data[off: off + (1 << int(flat.leaf_rank[l]))]).sum()), 1.0))
+            residues, moduli = [], []
+            value, passes = None, 0
+            need = max(1, math.ceil(bits / math.log2(EXACT_PRIMES[-1])))
+            while True:
+                if len(moduli) >= len(EXACT_PRIMES):
+                    raise OverflowError("count needs more than %d primes" % len(EXACT_PRIMES))
+                p = EXACT_PRIMES[len(moduli)]
+                r = one_pass(np.mod(flat.leaf_data, p), p)
+                passes += 1
+                if r != int(r) or not (0 <= r < p * max(world, 1)):
+                    raise RuntimeError("exact mode: residue %r is not an integer below the modulus" % r)
+                residues.append(int(r) % p)
+                moduli.append(p)
+                if len(moduli) < need:
+                    continue
+                x = crt(residues, moduli)
+                m = math.prod(moduli)
+                if x > m // 2 and (not math.isfinite(estimate) or estimate < 0):
+                    x -= m  # symmetric range for negative totals
+                # stable (the last prime did not change the reconstruction) and consistent with the float64 pass
+                prev = crt(residues[:-1], moduli[:-1]) if len(moduli) > 1 else None
+                if prev is not None and prev > math.prod(moduli[:-1]) // 2 and x < 0:
+                    prev -= math.prod(moduli[:-1])
+                close = (not math.isfinite(estimate)) or abs(x - estimate) <= 1e-6 * abs(estimate) + 1.0
+                if close and (prev == x or len(moduli) == 1 and abs(x) < m // 4):
+                    value = x
+                    break
+            self.last_stats = {"exact_passes": passes, "primes": list(moduli), "float_estimate": estimate,
+                               "seconds": time.perf_counter() - t0, "slices": total, "rank": rank, "world": world,
+                               "launches": compiled.interruptible_stats["launches"]}
+        finally:
+            compiled.close()
+        return value
 
     # ---- secondary entries ----
     def contract(self, network, contraction_tree):

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -74,6 +75,7 @@ struct tob_plan {
     int64_t last_gemm_launches = 0;
     double slice_flops = 0;
     bool time_gemm = false;
+    double modulus = 0.0;  // exact mode: prime modulus (< 2^23), 0 = float64 arithmetic
 };
 
 static bool g_configured[64] = {false};  // per device: kernel attributes live in the device's context
@@ -511,6 +513,8 @@ static KParams make_params(const tob_plan* p, const Lane& L, const Op& op) {
     k.mask_n = ~op.mask_m & (tot >= 64 ? ~0ull : ((1ull << tot) - 1ull));
     k.runs_m = make_runs(k.mask_m);
     k.runs_n = make_runs(k.mask_n);
+    k.modp = p->modulus;
+    k.inv_modp = p->modulus > 0.0 ? 1.0 / p->modulus : 0.0;
     return k;
 }
 
@@ -527,7 +531,7 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
         for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
         const int smem_ops = std::min(max_ops, (int)(64 * 1024 / sizeof(MicroOpDev)));
         return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops,
-                                p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, L.stream);
+                                p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, p->modulus, L.stream);
     }
     KParams k = make_params(p, L, op);
     return launch_contract(op, k, L.stream, launches);
@@ -657,7 +661,7 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
             CUDA_TRY(cudaEventRecord(p->lane[l].ev_b, p->lane[l].stream));
             CUDA_TRY(cudaStreamWaitEvent(L0.stream, p->lane[l].ev_b, 0));
         }
-        CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, (int)batch, initial, first_batch ? 0 : 1, L0.stream));
+        CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, (int)batch, initial, first_batch ? 0 : 1, p->modulus, L0.stream));
         launches++;
         done += batch;
         first_batch = false;
@@ -680,6 +684,16 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     p->last_gemm_launches = (int64_t)n_gemm;
     *result = *p->h_readback;
     p->runs++;
+    return TOB_OK;
+}
+
+int tob_plan_set_modulus(tob_plan* p, double modulus) {
+    if (!p) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (modulus != 0.0 && !(modulus >= 2.0 && modulus < 8388608.0 && modulus == floor(modulus))) {
+        set_error("modulus must be 0 or an integer in [2, 2^23)");
+        return TOB_E_INVALID;
+    }
+    p->modulus = modulus;
     return TOB_OK;
 }
 
@@ -738,7 +752,7 @@ int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_op
         i++;
     }
     CUDA_TRY(cudaEventRecord(ev[i], L0.stream));
-    CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, 1, 0.0, 0, L0.stream));
+    CUDA_TRY(launch_final_sum(p->d_acc, p->d_results, 1, 0.0, 0, p->modulus, L0.stream));
     CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_acc, sizeof(double), cudaMemcpyDeviceToHost, L0.stream));
     CUDA_TRY(cudaStreamSynchronize(L0.stream));
     for (int64_t j = 0; j < n_ops; j++) CUDA_TRY(cudaEventElapsedTime(&ms_per_op[j], ev[j], ev[j + 1]));
@@ -881,6 +895,8 @@ int tob_tensordot_device(const double* a, int32_t rank_a, const double* b, int32
     kp.mask_n = tot == 0 ? 0ull : (~op.mask_m & (tot >= 64 ? ~0ull : ((1ull << tot) - 1ull)));
     kp.runs_m = make_runs(kp.mask_m);
     kp.runs_n = make_runs(kp.mask_n);
+    kp.modp = 0.0;
+    kp.inv_modp = 0.0;
     int launches = 0;
     CUDA_TRY(launch_contract(op, kp, stream, &launches));
     if (ms) {

@@ -57,6 +57,15 @@ __device__ __forceinline__ const double* operand_base(const double* base, const 
     return (leaf >= 0) ? base + leaf_off[leaf] : base;
 }
 
+// x mod p for an integer-valued 0 <= x < 2^53 (exact: the quotient estimate is off by at most one)
+__device__ __forceinline__ double mod_reduce(double x, double p, double inv_p) {
+    const double q = floor(x * inv_p);
+    double r = fma(-q, p, x);
+    if (r < 0.0) r += p;
+    if (r >= p) r -= p;
+    return r;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(256) k_generic_t1(KParams p) {
                 s = fma(x.y, y.y, s);
             }
         }
+        if (p.modp > 0.0) s = mod_reduce(s, p.modp, p.inv_modp);  // K <= 64 products < 2^46: exact so far
         p.c[c] = s;
     }
 }
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256) k_generic_t1x4(KParams p) {
                     }
                 }
             }
-            out[j] = s;
+            out[j] = (p.modp > 0.0) ? mod_reduce(s, p.modp, p.inv_modp) : s;
         }
         double2* dst = reinterpret_cast<double2*>(p.c + c0);
         dst[0] = make_double2(out[0], out[1]);
@@ -181,7 +191,13 @@ __global__ void __launch_bounds__(256) k_generic_t32(KParams p) {
             s0 = fma(x.x, y.x, s0);
             s1 = fma(x.y, y.y, s1);
         }
-        const double s = warp_sum(s0 + s1);
+        double s;
+        if (p.modp > 0.0) {  // <= 32 products per accumulator (k <= 11), then 32 residues per warp sum
+            s = warp_sum(mod_reduce(s0, p.modp, p.inv_modp) + mod_reduce(s1, p.modp, p.inv_modp));
+            s = mod_reduce(s, p.modp, p.inv_modp);
+        } else {
+            s = warp_sum(s0 + s1);
+        }
         if (lane == 0) p.c[c] = s;
     }
 }
@@ -214,19 +230,28 @@ __global__ void __launch_bounds__(256) k_generic_t256(KParams p) {
             s1 = fma(x1.x, y1.x, s1); s1 = fma(x1.y, y1.y, s1);
             s2 = fma(x2.x, y2.x, s2); s2 = fma(x2.y, y2.y, s2);
             s3 = fma(x3.x, y3.x, s3); s3 = fma(x3.y, y3.y, s3);
+            if (p.modp > 0.0 && (((i >> 10) & 31) == 31)) {  // every 32 iterations: 64 products per accumulator
+                s0 = mod_reduce(s0, p.modp, p.inv_modp); s1 = mod_reduce(s1, p.modp, p.inv_modp);
+                s2 = mod_reduce(s2, p.modp, p.inv_modp); s3 = mod_reduce(s3, p.modp, p.inv_modp);
+            }
         }
         for (; i < chunk2; i += 256) {
             const double2 x = a2[i], y = b2[i];
             s0 = fma(x.x, y.x, s0);
             s0 = fma(x.y, y.y, s0);
         }
-        double s = warp_sum((s0 + s1) + (s2 + s3));
+        if (p.modp > 0.0) {
+            s0 = mod_reduce(s0, p.modp, p.inv_modp); s1 = mod_reduce(s1, p.modp, p.inv_modp);
+            s2 = mod_reduce(s2, p.modp, p.inv_modp); s3 = mod_reduce(s3, p.modp, p.inv_modp);
+        }
+        double s = warp_sum((s0 + s1) + (s2 + s3));  // 128 residues: far below 2^53
         __syncthreads();  // red[] reuse across iterations of the work loop
         if (lane == 0) red[warp] = s;
         __syncthreads();
         if (warp == 0) {
             s = (lane < 8) ? red[lane] : 0.0;
             s = warp_sum(s);
+            if (p.modp > 0.0) s = mod_reduce(s, p.modp, p.inv_modp);
             if (lane == 0) {
                 if (ks > 0) p.ws[split * outs + c] = s;
                 else p.c[c] = s;
@@ -237,11 +262,11 @@ __global__ void __launch_bounds__(256) k_generic_t256(KParams p) {
 
 // C[o] = sum_j ws[j * outs + o], j ascending (deterministic)
 __global__ void __launch_bounds__(256) k_reduce_splits(const double* __restrict__ ws, double* __restrict__ c,
-                                                      unsigned long long outs, int nsplit) {
+                                                      unsigned long long outs, int nsplit, double modp, double inv_modp) {
     for (unsigned long long o = blockIdx.x * 256ull + threadIdx.x; o < outs; o += (unsigned long long)gridDim.x * 256ull) {
         double s = ws[o];
         for (int j = 1; j < nsplit; j++) s += ws[(unsigned long long)j * outs + o];
-        c[o] = s;
+        c[o] = (modp > 0.0) ? mod_reduce(s, modp, inv_modp) : s;  // <= 1024 residues: exact
     }
 }
 
@@ -374,6 +399,16 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
             for (int i = 0; i < MB; i++)
 #pragma unroll
                 for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+        // exact mode: at most 128 products (< 2^46 each) per accumulator between reductions
+        if (p.modp > 0.0 && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    acc[i][j][0] = mod_reduce(acc[i][j][0], p.modp, p.inv_modp);
+                    acc[i][j][1] = mod_reduce(acc[i][j][1], p.modp, p.inv_modp);
+                }
         }
     }
     cp_async_wait<0>();
@@ -569,6 +604,16 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
         }
         __syncwarp();                       // every lane's fragment loads of this stage have been consumed
         if (lane == 0) mbar_arrive(&empty[s]);
+        // exact mode: at most 128 products (< 2^46 each) per accumulator between reductions
+        if (p.modp > 0.0 && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    acc[i][j][0] = mod_reduce(acc[i][j][0], p.modp, p.inv_modp);
+                    acc[i][j][1] = mod_reduce(acc[i][j][1], p.modp, p.inv_modp);
+                }
+        }
     }
 
     // ---- epilogue (identical to k_gemm_dmma) ----
@@ -615,7 +660,7 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_WZ4 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 4>
 
 __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
-                            double* arena, const double* arena0, const long long* leaf_off, int smem_ops);
+                            double* arena, const double* arena0, const long long* leaf_off, int smem_ops, double modp);
 
 cudaError_t configure_kernels() {
     cudaError_t e;
@@ -672,10 +717,10 @@ __global__ void k_accum(DevState* st, const double* root, const long long* leaf_
 
 // acc = (previous acc | initial) + results[0] + results[1] + ...   sequentially, exactly like the
 // reference's `result += tensor_result[()]` loop (base_api.py:25-27)
-__global__ void k_final_sum(double* acc, const double* results, int count, double initial, int use_previous) {
+__global__ void k_final_sum(double* acc, const double* results, int count, double initial, int use_previous, double modp) {
     double s = use_previous ? acc[0] : initial;
-    for (int i = 0; i < count; i++) s += results[i];
-    acc[0] = s;
+    for (int i = 0; i < count; i++) s += results[i];  // exact mode: <= 4096 residues + one residue: exact
+    acc[0] = (modp > 0.0) ? mod_reduce(s, modp, 1.0 / modp) : s;
 }
 
 cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream) {
@@ -689,9 +734,9 @@ cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf
     return cudaGetLastError();
 }
 
-cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous,
+cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous, double modp,
                              cudaStream_t stream) {
-    k_final_sum<<<1, 1, 0, stream>>>(acc, results, count, initial, use_previous);
+    k_final_sum<<<1, 1, 0, stream>>>(acc, results, count, initial, use_previous, modp);
     return cudaGetLastError();
 }
 
@@ -701,19 +746,28 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 // so a __syncthreads between joins is the only synchronisation.  Replaces hundreds of launch-bound
 // kernel launches per slice by one.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double micro_dot(const double* ar, const double* br, int k, bool a_glob, bool b_glob) {
-    if (k == 0) return (a_glob ? __ldcg(ar) : ar[0]) * (b_glob ? __ldcg(br) : br[0]);
+__device__ __forceinline__ double micro_dot(const double* ar, const double* br, int k, bool a_glob, bool b_glob, double modp) {
+    if (k == 0) {
+        const double s = (a_glob ? __ldcg(ar) : ar[0]) * (b_glob ? __ldcg(br) : br[0]);
+        return modp > 0.0 ? mod_reduce(s, modp, 1.0 / modp) : s;
+    }
     const double2* a2 = reinterpret_cast<const double2*>(ar);
     const double2* b2 = reinterpret_cast<const double2*>(br);
     const int K2 = 1 << (k - 1);
+    const double inv = modp > 0.0 ? 1.0 / modp : 0.0;
     double s0 = 0.0, s1 = 0.0;
     for (int j = 0; j < K2; j++) {
         const double2 x = a_glob ? __ldcg(a2 + j) : a2[j];
         const double2 y = b_glob ? __ldcg(b2 + j) : b2[j];
         s0 = fma(x.x, y.x, s0);
         s1 = fma(x.y, y.y, s1);
+        if (modp > 0.0 && (j & 63) == 63) {  // exact mode: reduce before 65 products pile up
+            s0 = mod_reduce(s0, modp, inv);
+            s1 = mod_reduce(s1, modp, inv);
+        }
     }
-    return s0 + s1;
+    const double s = s0 + s1;
+    return modp > 0.0 ? mod_reduce(s, modp, inv) : s;
 }
 
 // Shared memory: [join descriptors | leaf cache | two forward buffers].  The serial chain of joins a CTA
@@ -722,7 +776,7 @@ __device__ __forceinline__ double micro_dot(const double* ar, const double* br, 
 // latency instead of two L2 round trips (store result, load it back).
 __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
                                                    const double* leaves, double* arena, const double* arena0,
-                                                   const long long* leaf_off, int smem_ops) {
+                                                   const long long* leaf_off, int smem_ops, double modp) {
     extern __shared__ __align__(16) unsigned char micro_smem[];
     MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
     double* cache = reinterpret_cast<double*>(micro_smem + (size_t)smem_ops * sizeof(MicroOpDev));
@@ -771,7 +825,7 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
                 if ((mask >> b) & 1u) { mi |= bit << im; im++; }
                 else { ni |= bit << in; in++; }
             }
-            const double s = micro_dot(A + ((size_t)mi << k), B + ((size_t)ni << k), k, a_src == 0, b_src == 0);
+            const double s = micro_dot(A + ((size_t)mi << k), B + ((size_t)ni << k), k, a_src == 0, b_src == 0, modp);
             C[c] = s;
             if (fwd_out) mine[c] = s;
         }
@@ -780,9 +834,10 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
 }
 
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
-                             double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream) {
+                             double* arena, const double* arena0, const long long* leaf_off, double modp,
+                             cudaStream_t stream) {
     const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double);
-    k_microtree<<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops);
+    k_microtree<<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
     return cudaGetLastError();
 }
 
@@ -864,7 +919,7 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (op.ksplit_log2 > 0) {
-        k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2);
+        k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
         (*launches)++;
         e = cudaGetLastError();
     }

@@ -27,6 +27,9 @@ struct KParams {
     int32_t ksplit_log2;
     uint64_t mask_m, mask_n;
     BitRuns runs_m, runs_n;
+    // exact mode (entry type "bigint"): every tensor holds residues modulo the prime `modp` < 2^23 as
+    // doubles; sums of up to 128 products stay below 2^53 and are exact, then get reduced.  0 = float64.
+    double modp, inv_modp;
 };
 
 // One join of a micro subtree (device copy).  m + n <= 12, operands <= 2^12 doubles.
@@ -78,10 +81,11 @@ struct PermuteParams {
 
 cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
-                             double* arena, const double* arena0, const long long* leaf_off, cudaStream_t stream);
+                             double* arena, const double* arena0, const long long* leaf_off, double modp,
+                             cudaStream_t stream);
 cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results,
                          cudaStream_t stream);
-cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous,
+cudaError_t launch_final_sum(double* acc, const double* results, int count, double initial, int use_previous, double modp,
                              cudaStream_t stream);
 cudaError_t launch_begin_slice(DevState* st, SliceTables t, cudaStream_t stream);
 cudaError_t launch_permute(const double* in, double* out, int rank, const int32_t* src_bit, cudaStream_t stream);

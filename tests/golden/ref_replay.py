@@ -7,6 +7,8 @@ connected in edge-id order), `ContractionTreeContext.leaf/join`, `SlicedExecutio
 build of /root/reference made by make_golden.py).
 
 Usage: python tests/golden/ref_replay.py NAME[:VARIANT] [...]      (writes expected.count into the fixture)
+       python tests/golden/ref_replay.py --bigint NAME[:VARIANT] [...]   (reference `--entry_type=bigint`:
+                                                   exact Python-int count -> expected.count_exact, a decimal string)
 """
 import os
 import sys
@@ -17,7 +19,7 @@ sys.path.insert(0, HERE)
 import make_golden as mg  # noqa: E402
 
 
-def to_reference_plan(R, pp):
+def to_reference_plan(R, pp, as_int=False):
     import numpy as np
     from contraction_methods.contraction_tree import ContractionTreeContext
     from tensor_network.tensor import BuiltTensor
@@ -27,6 +29,9 @@ def to_reference_plan(R, pp):
     slots = []
     for t in pp.tensors:
         arr = np.array(t["data"], dtype=np.float64).reshape(t["shape"])
+        if as_int:  # exact replays: Python ints in an object array, like the reference's own bigint leaves
+            assert np.array_equal(arr, np.rint(arr))
+            arr = np.array([int(x) for x in arr.reshape(-1)], dtype=object).reshape(t["shape"])
         slots.append(net.add_node(BuiltTensor(arr)))
     for e, (t1, t2) in enumerate(pp.edges):
         a1 = pp.index_lists[t1].index(e)
@@ -54,13 +59,28 @@ def main():
 
     mg.ensure_reference_build()
     R = mg.import_reference()
-    for spec in sys.argv[1:]:
+    bigint = "--bigint" in sys.argv
+    for spec in [a for a in sys.argv[1:] if a != "--bigint"]:
         name, _, variant = spec.partition(":")
         path = os.path.join(HERE, name + ".json.gz")
         pp = PortablePlan.load(path)
         target = pp.variant(variant) if variant else pp
-        plan = to_reference_plan(R, target)
+        plan = to_reference_plan(R, target, as_int=bigint)
         t0 = time.time()
+        if bigint:
+            api = R["tensor_network"].ALL_APIS["numpy"]()
+            api.add_argument("entry_type", "bigint")
+            exact = api.contract_sliced(plan)
+            assert isinstance(exact, int), type(exact)
+            pp = PortablePlan.load(path)
+            rec = {"count_exact": str(exact), "count_exact_source": "reference numpy backend, --entry_type=bigint"}
+            if variant:
+                [v for v in pp.variants if v["name"] == variant][0]["expected"].update(rec)
+            else:
+                pp.expected.update(rec)
+            pp.save(path)
+            print("%s: exact count=%d  [%.1fs]" % (spec, exact, time.time() - t0), flush=True)
+            continue
         count, dt, _ = mg.reference_contract(R, plan)
         rec = {"count": count, "count_hex": float(count).hex(), "numpy_seconds_buildbox_8c": dt,
                "count_source": "tests/golden/ref_replay.py (reference numpy executor on the stored plan)"}

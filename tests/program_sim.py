@@ -42,7 +42,8 @@ def upload_leaves(desc, flat):
     return dev
 
 
-def run_program(desc, flat, first=0, count=None, stride=1):
+def run_program(desc, flat, first=0, count=None, stride=1, modulus=0):
+    """modulus > 0: the exact mode — every op reduces modulo the prime (done here in int64, exact)."""
     S = desc["n_slice_groups"]
     if count is None:
         count = ((1 << S) - first + stride - 1) // stride
@@ -62,6 +63,8 @@ def run_program(desc, flat, first=0, count=None, stride=1):
         nonlocal acc
         if op["kind"] == 2:
             acc += operand(op["a"], 1)[0]
+            if modulus:
+                acc %= modulus
             return
         if op["kind"] == 3:  # micro-subtree launch: every join of every CTA, in CTA order
             assert op["cta_start"][0] == 0 and op["cta_start"][-1] == len(op["micro"])
@@ -73,7 +76,10 @@ def run_program(desc, flat, first=0, count=None, stride=1):
         A = operand(op["a"], 1 << (m + k)).reshape(1 << m, 1 << k)
         B = operand(op["b"], 1 << (n + k)).reshape(1 << n, 1 << k)
         assert not np.isnan(A).any() and not np.isnan(B).any(), "operand read before written / after freed"
-        Cm = A @ B.T
+        if modulus:
+            Cm = ((A.astype(np.int64) @ B.T.astype(np.int64)) % modulus).astype(np.float64)
+        else:
+            Cm = A @ B.T
         mask_m = op["mask_m"]
         mask_n = ~mask_m & ((1 << (m + n)) - 1)
         addr = pdep_table(m, mask_m)[:, None] | pdep_table(n, mask_n)[None, :]
