@@ -17,7 +17,9 @@ objects and are spread over the ranks (longest first); one NCCL all-reduce combi
 
   value : inputs resident in HBM (plans compiled, leaves uploaded) when the timed region starts;
           timed with CUDA events on the stream the kernels run on, one event pair per step, an L2
-          flush between steps, MAX over ranks per step.
+          flush between steps, MAX over ranks per step.  Per-GEMM event timing is ON in this arm (it feeds
+          `roofline`): GEMMs of the two slice lanes are then chained, which costs ~3 % on the sliced
+          mid-size instances compared with the default (untimed) path the e2e arm runs.
   e2e   : the same workload through the reference-facing call `B200API.contract_sliced(plan)` with
           HOST leaf buffers: flatten + plan compile + arena allocation + pinned H2D of the leaves +
           kernels + D2H of the count inside the timed region, every step.
