@@ -389,7 +389,9 @@ class B200API:
         keep = self._distributed
         self._distributed = False
         try:
-            return np.array(self.contract_sliced(plan), dtype=np.float64)
+            value = self.contract_sliced(plan)
+            # 0-d array so `result[tuple()]` works; exact mode keeps the Python int (object dtype)
+            return np.array(value, dtype=object if self._entry_type == "bigint" else np.float64)
         finally:
             self._distributed = keep
 
