@@ -78,6 +78,15 @@ struct tob_plan {
     double modulus = 0.0;  // exact mode: prime modulus (< 2^23), 0 = float64 arithmetic
 };
 
+// CUDA events released on every exit path of the stand-alone entry points
+struct EventSet {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~EventSet() {
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
 static bool g_configured[64] = {false};  // per device: kernel attributes live in the device's context
 
 // ------------------------------------------------------------------------------------------------
@@ -779,19 +788,17 @@ int tob_permute_device(const double* in, double* out, int32_t rank, const int32_
         seen[perm[j]] = 1;
         src_bit[rank - 1 - j] = rank - 1 - perm[j];
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EventSet es;
     if (ms) {
-        CUDA_TRY(cudaEventCreate(&e0));
-        CUDA_TRY(cudaEventCreate(&e1));
-        CUDA_TRY(cudaEventRecord(e0, stream));
+        CUDA_TRY(cudaEventCreate(&es.ev[0]));
+        CUDA_TRY(cudaEventCreate(&es.ev[1]));
+        CUDA_TRY(cudaEventRecord(es.ev[0], stream));
     }
     CUDA_TRY(launch_permute(in, out, rank, src_bit, stream));
     if (ms) {
-        CUDA_TRY(cudaEventRecord(e1, stream));
-        CUDA_TRY(cudaEventSynchronize(e1));
-        CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        CUDA_TRY(cudaEventRecord(es.ev[1], stream));
+        CUDA_TRY(cudaEventSynchronize(es.ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(ms, es.ev[0], es.ev[1]));
     }
     return TOB_OK;
 }
@@ -859,9 +866,10 @@ int tob_tensordot_device(const double* a, int32_t rank_a, const double* b, int32
         set_error("tensordot needs a workspace of at least " + std::to_string(need) + " bytes for the operand permutations");
         return TOB_E_INVALID;
     }
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    EventSet es;
+    cudaEvent_t* ev = es.ev;
     if (ms) {
-        for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+        for (int i = 0; i < 3; i++) CUDA_TRY(cudaEventCreate(&ev[i]));
         CUDA_TRY(cudaEventRecord(ev[0], stream));
     }
     auto run_permute = [&](const double* src, double* dst, int rank, const std::vector<int32_t>& perm) -> cudaError_t {
@@ -905,7 +913,6 @@ int tob_tensordot_device(const double* a, int32_t rank_a, const double* b, int32
         CUDA_TRY(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));  // permutations
         CUDA_TRY(cudaEventElapsedTime(&ms[1], ev[1], ev[2]));  // contraction
         ms[2] = (float)op.kind;
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
     }
     return TOB_OK;
 }
