@@ -294,7 +294,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // K step per pipeline stage (doubles) and the padded shared-memory row stride: stride == 4 (mod 16)
 // makes the 8x4 DMMA fragment loads (LDS.64) conflict-free for both TK = 16 and TK = 32.
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB>
+// EXACT: the residue-arithmetic instantiation (entry type bigint); the float64 instantiation carries none
+// of its code (the extra live values cost registers the two-CTAs-per-SM budget does not have)
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB, bool EXACT = false>
 __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NT = WM * WN * 32;             // threads per CTA
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
                 for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
         // exact mode: at most 128 products (< 2^46 each) per accumulator between reductions
-        if (p.modp > 0.0 && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
+        if (EXACT && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
 #pragma unroll
             for (int i = 0; i < MB; i++)
 #pragma unroll
@@ -474,7 +476,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
 // SWZ: dense 128-byte rows with the 16-byte chunk index XOR-ed by ((row & 3) << 1) instead of the padded
 // 160-byte rows: the 8x4 fragment loads stay conflict-free and a stage shrinks from 30 KB to 24 KB, so FOUR
 // stages fit twice per SM (ncu showed consumers waiting on `full` 24 % of the time with three).
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK, bool SWZ, int NPROD = 1>
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool BULK, bool SWZ, int NPROD = 1, bool EXACT = false>
 __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_ws(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NC = WM * WN * 32;  // consumer threads
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
         __syncwarp();                       // every lane's fragment loads of this stage have been consumed
         if (lane == 0) mbar_arrive(&empty[s]);
         // exact mode: at most 128 products (< 2^46 each) per accumulator between reductions
-        if (p.modp > 0.0 && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
+        if (EXACT && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
 #pragma unroll
             for (int i = 0; i < MB; i++)
 #pragma unroll
@@ -658,6 +660,10 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_WZ k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 #define GEMM_76_WZ4 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 4>
+// residue-arithmetic instantiations (entry type bigint)
+#define GEMM_76_X k_gemm_dmma<7, 6, 4, 2, 16, 3, 2, true>
+#define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
+#define GEMM_76_WZ2_X k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2, true>
 
 __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
                             double* arena, const double* arena0, const long long* leaf_off, int smem_ops, double modp);
@@ -683,6 +689,12 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_WZ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_66_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_WZ2_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_microtree, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
@@ -858,7 +870,17 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         const unsigned long long tiles = 1ull << ((op.m - op.tm_log2) + (op.n - op.tn_log2));
         const unsigned long long blocks = tiles << op.ksplit_log2;
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        if (op.tm_log2 == 7 && op.tn_log2 == 7) {
+        if (p.modp > 0.0) {
+            // exact mode: residue-arithmetic instantiations of the default kernels
+            if (op.tm_log2 == 7 && op.tn_log2 == 6 && (op.k - op.ksplit_log2) >= 8)
+                GEMM_76_WZ2_X<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
+            else if (op.tm_log2 == 7 && op.tn_log2 == 6)
+                GEMM_76_X<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+            else if (op.tm_log2 == 6 && op.tn_log2 == 6)
+                GEMM_66_X<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
+            else
+                return cudaErrorInvalidConfiguration;  // 128x128 experiment variants have no exact instantiation
+        } else if (op.tm_log2 == 7 && op.tn_log2 == 7) {
             const int v = gemm_variant();
             const bool k32 = (op.k - op.ksplit_log2) >= 5;  // the TK=32 variants need >= 32 K elements per split
             if (v == 2 && k32)
