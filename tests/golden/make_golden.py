@@ -83,6 +83,19 @@ def cubic_vc_cnf(n, seed):
     return "\n".join(lines) + "\n"
 
 
+def random_kcnf(n_vars, n_clauses, k, seed):
+    """Uniform random k-CNF (distinct variables per clause, random signs): leaves of higher rank than the
+    cubic family has (a variable tensor's rank is its number of occurrences)."""
+    import numpy
+    rng = numpy.random.default_rng(seed)
+    lines = ["p cnf %d %d" % (n_vars, n_clauses)]
+    for _ in range(n_clauses):
+        vs = rng.choice(n_vars, size=k, replace=False) + 1
+        signs = rng.integers(0, 2, size=k) * 2 - 1
+        lines.append(" ".join(str(int(v * s)) for v, s in zip(vs, signs)) + " 0")
+    return "\n".join(lines) + "\n"
+
+
 def mcc_weight_lines(n, rng_seed):
     import numpy
     rng = numpy.random.default_rng(rng_seed)
@@ -192,6 +205,8 @@ def make_fixture(R, name, cnf_text, weights, planner, seed, timeout, slicings, c
             "reference": "vardigroup/TensorOrder numpy backend, float64"}
     meta.update(meta_extra or {})
     plan = fresh_plan(R, base)
+    if contract and plan.memory > 3e8:
+        raise RuntimeError("%s: best plan needs %.3g entries; refusing to contract it with numpy" % (name, plan.memory))
     pp = export_plan(plan, name, meta=meta, with_tree_check=tree_check)
     add_params(R, pp, plan.network)
     if contract:
@@ -293,6 +308,15 @@ def main():
                 einsum=True)
     job("toy_3cnf_mcc", cnf=TOY_CNFS["toy_3cnf"] + mcc_weight_lines(6, 6), weights="mcc", planner="factor-Flow",
         seed=1, timeout=2, slicings=[{"name": "min2", "minimum_slice": 2}], einsum=True)
+    # --- other CNF shapes: random 3-CNF / 4-CNF (variable tensors of rank ~6-10, clause tensors of rank 3-4) ---
+    job("rand3cnf_24_lineflow", cnf=random_kcnf(24, 40, 3, 30), weights="unweighted", planner="line-Flow", seed=1,
+        timeout=3, slicings=[{"name": "min3", "minimum_slice": 3}], tree_check=False)
+    job("rand3cnf_24_factorflow", cnf=random_kcnf(24, 40, 3, 30), weights="unweighted", planner="factor-Flow", seed=1,
+        timeout=3, slicings=[{"name": "min3", "minimum_slice": 3}], tree_check=False)
+    job("rand3cnf_16_lineflow", cnf=random_kcnf(16, 30, 3, 5), weights="unweighted", planner="line-Flow", seed=1,
+        timeout=3, slicings=[{"name": "min4", "minimum_slice": 4}], tree_check=False)
+    job("rand4cnf_18_mcc_lineflow", cnf=random_kcnf(18, 24, 4, 24) + mcc_weight_lines(18, 24), weights="mcc",
+        planner="line-Flow", seed=1, timeout=3, slicings=[{"name": "min2", "minimum_slice": 2}], tree_check=False)
     # --- config 2: the family ---
     for n in range(60, args.max_plan_n + 1, 10):
         timeout = 5 if n <= 100 else (10 if n <= 150 else 20)
