@@ -73,6 +73,9 @@ typedef struct {
                              /* (one CTA per subtree); 0: one launch per join                              */
     int32_t slice_lanes;     /* slices in flight at once, each with its own arena/workspace/stream:        */
                              /* 0 (default) = 2 when the second arena costs <= 2 GiB, else 1; 1; 2          */
+    int32_t dag_branches;    /* joins of independent subtrees run concurrently on up to this many streams   */
+                             /* per lane (fork/join by events; captured into the slice graph as a DAG):     */
+                             /* 0 (default) = 16; 1 = one stream, strict post-order                          */
 } tob_options;
 
 void tob_default_options(tob_options* opt);

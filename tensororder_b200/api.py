@@ -68,7 +68,7 @@ class CompiledPlan:
 
     def __init__(self, flat: FlatPlan, device: int = 0, use_graph=None, kernel_policy: int = 0,
                  hoist_invariant: bool = True, mem_limit_bytes: int = 0, use_microtree: bool = True,
-                 slice_lanes: int = 0):
+                 slice_lanes: int = 0, dag_branches: int = 0):
         self.flat = flat
         self._handle = c_void_p()
         desc = cabi.tob_plan_desc()
@@ -93,6 +93,7 @@ class CompiledPlan:
         opt.mem_limit_bytes = int(mem_limit_bytes)
         opt.use_microtree = 1 if use_microtree else 0
         opt.slice_lanes = int(slice_lanes)
+        opt.dag_branches = int(dag_branches)
         rc = cabi.lib.tob_plan_create(byref(desc), byref(opt), byref(self._handle))
         if rc != cabi.TOB_OK:
             raise ValueError("tob_plan_create: " + cabi.last_error())
@@ -226,6 +227,7 @@ class B200API:
         self._hoist = True
         self._microtree = True
         self._lanes = 0
+        self._branches = 0
         self._distributed = True
         self.last_stats = {}
 
@@ -249,6 +251,8 @@ class B200API:
             self._hoist = bool(value)
         elif key == "slice_lanes":
             self._lanes = int(value)
+        elif key == "dag_branches":
+            self._branches = int(value)
         elif key == "use_microtree":
             self._microtree = bool(value)
         elif key == "distributed":
@@ -280,7 +284,8 @@ class B200API:
         rank, world = self._rank_world()
         compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
                                 kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
-                                use_microtree=self._microtree, slice_lanes=self._lanes)
+                                use_microtree=self._microtree, slice_lanes=self._lanes,
+                                dag_branches=self._branches)
         try:
             t1 = time.perf_counter()
             compiled.upload()
@@ -320,7 +325,8 @@ class B200API:
         rank, world = self._rank_world()
         compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
                                 kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
-                                use_microtree=self._microtree, slice_lanes=self._lanes)
+                                use_microtree=self._microtree, slice_lanes=self._lanes,
+                                dag_branches=self._branches)
         try:
             total = compiled.num_slices
             if num_slice_limit is not None:

@@ -38,6 +38,7 @@ class tob_options(ctypes.Structure):
         ("mem_limit_bytes", c_int64),
         ("use_microtree", c_int32),
         ("slice_lanes", c_int32),
+        ("dag_branches", c_int32),
     ]
 
 

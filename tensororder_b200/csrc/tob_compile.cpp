@@ -95,23 +95,37 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
 // Offline arena allocator (first fit, lowest address), sizes in doubles
 // ------------------------------------------------------------------------------------------------
 struct Arena {
-    std::map<int64_t, int64_t> free_;  // offset -> size
-    int64_t top = 0;                   // high-water mark
-    int64_t alloc(int64_t size) {
+    // A free block remembers which joins released its pieces, as the range [tmin, tmax] of their post-order
+    // positions (empty range = released before the last barrier: safe for everyone).  A join whose subtree
+    // covers that range already depends on those joins, so reusing the block adds no ordering edge to the
+    // DAG schedule; any other reuse would serialise two independent subtrees (WAR) — for small tensors
+    // the arena grows instead, for large ones memory wins and the false dependency is accepted.
+    struct Free { int64_t size; int32_t tmin, tmax; };
+    std::map<int64_t, Free> free_;  // offset -> block
+    int64_t top = 0;                // high-water mark
+    static constexpr int64_t kSmall = (int64_t)1 << 17;  // doubles: below this never take an unrelated block
+    static bool safe(const Free& f, int32_t lo, int32_t hi) { return f.tmin > f.tmax || (f.tmin >= lo && f.tmax <= hi); }
+    int64_t take(std::map<int64_t, Free>::iterator it, int64_t size) {
+        const int64_t off = it->first;
+        Free rest = it->second;
+        rest.size -= size;
+        free_.erase(it);
+        if (rest.size > 0) free_[off + size] = rest;
+        return off;
+    }
+    // [lo, hi]: post-order range of the allocating join's subtree (joins it transitively depends on)
+    int64_t alloc(int64_t size, int32_t lo = 0, int32_t hi = -1, bool dag = false) {
         size = round_up(std::max<int64_t>(size, 1), kAlign);
-        for (auto it = free_.begin(); it != free_.end(); ++it) {
-            if (it->second >= size) {
-                int64_t off = it->first;
-                int64_t rest = it->second - size;
-                free_.erase(it);
-                if (rest > 0) free_[off + size] = rest;
-                return off;
-            }
-        }
-        // extend: if the last free block touches the top, grow it
+        if (dag)
+            for (auto it = free_.begin(); it != free_.end(); ++it)
+                if (it->second.size >= size && safe(it->second, lo, hi)) return take(it, size);
+        if (!dag || size > kSmall)
+            for (auto it = free_.begin(); it != free_.end(); ++it)
+                if (it->second.size >= size) return take(it, size);
+        // extend: if the last free block touches the top (and may be used), grow it
         if (!free_.empty()) {
             auto last = std::prev(free_.end());
-            if (last->first + last->second == top) {
+            if (last->first + last->second.size == top && (!dag || size > kSmall || safe(last->second, lo, hi))) {
                 int64_t off = last->first;
                 free_.erase(last);
                 top = off + size;
@@ -122,23 +136,146 @@ struct Arena {
         top += size;
         return off;
     }
-    void release(int64_t off, int64_t size) {
+    void release(int64_t off, int64_t size, int32_t tag = -1) {
         size = round_up(std::max<int64_t>(size, 1), kAlign);
-        auto it = free_.emplace(off, size).first;
+        Free f{size, tag < 0 ? 1 : tag, tag < 0 ? 0 : tag};
+        auto merge = [](Free& a, const Free& b) {
+            a.size += b.size;
+            if (b.tmin <= b.tmax) {
+                if (a.tmin > a.tmax) { a.tmin = b.tmin; a.tmax = b.tmax; }
+                else { a.tmin = std::min(a.tmin, b.tmin); a.tmax = std::max(a.tmax, b.tmax); }
+            }
+        };
+        auto it = free_.emplace(off, f).first;
         auto nx = std::next(it);
-        if (nx != free_.end() && it->first + it->second == nx->first) {
-            it->second += nx->second;
+        if (nx != free_.end() && it->first + it->second.size == nx->first) {
+            merge(it->second, nx->second);
             free_.erase(nx);
         }
         if (it != free_.begin()) {
             auto pv = std::prev(it);
-            if (pv->first + pv->second == it->first) {
-                pv->second += it->second;
+            if (pv->first + pv->second.size == it->first) {
+                merge(pv->second, it->second);
                 free_.erase(it);
             }
         }
     }
+    void barrier() {  // everything released so far is ordered before whatever comes next
+        for (auto& kv : free_) { kv.second.tmin = 1; kv.second.tmax = 0; }
+    }
 };
+
+// ------------------------------------------------------------------------------------------------
+// DAG schedule of one op list.  The contraction tree's joins form a forest of dependencies of depth
+// ~20 for trees of 200+ joins (line-graph plans are caterpillars hanging off a few long spines), but one
+// stream runs them as a chain and every launch-bound join then costs a full dependent-launch latency.
+// Ops are spread over `max_branches` streams: an op follows one of its producers on that producer's
+// stream when it can, independent subtrees start on a free stream, and every other ordering the
+// sequential program relied on becomes an explicit wait:
+//   RAW  the producers of both operands,
+//   WAR/WAW  every earlier op that read or wrote arena space the result overwrites (the offline arena
+//        reuses space along the post-order),
+//   the split-K workspace (one per lane) serialises its users.
+// OP_MICRO and OP_ACCUM are barriers (the executor joins all branches before them and forks after).
+// ------------------------------------------------------------------------------------------------
+int schedule_branches(std::vector<Op>* list_p, int max_branches) {
+    std::vector<Op>& list = *list_p;
+    const int n = (int)list.size();
+    for (Op& op : list) { op.branch = 0; op.signal = 0; op.waits.clear(); }
+    if (max_branches <= 1 || n < 3) return 1;
+    const int B = std::min(max_branches, 32);
+    std::map<int32_t, int32_t> idx_of_node;
+    for (int j = 0; j < n; j++)
+        if (list[j].kind == OP_GENERIC || list[j].kind == OP_GEMM) idx_of_node[list[j].node] = j;
+    auto producer = [&](const OperandRef& r) -> int {
+        if (r.space == 0) return -1;
+        auto it = idx_of_node.find(r.node);
+        return it == idx_of_node.end() ? -1 : it->second;
+    };
+    std::vector<int32_t> consumer(n, -1);
+    for (int j = 0; j < n; j++) {
+        if (list[j].kind != OP_GENERIC && list[j].kind != OP_GEMM) continue;
+        for (const OperandRef* r : {&list[j].a, &list[j].b}) {
+            const int pi = producer(*r);
+            if (pi >= 0) consumer[pi] = j;
+        }
+    }
+    struct Rec { int64_t lo, hi; int32_t op; };
+    std::vector<Rec> recs;          // arena regions touched by earlier ops (since the last barrier)
+    std::vector<int32_t> tail(B, -1);                     // last op of each branch
+    std::vector<char> is_free(B, 1);                      // tail already consumed elsewhere (or unused)
+    std::vector<std::vector<int32_t>> waited(B, std::vector<int32_t>(B, -1));
+    int barrier = -1, last_ws = -1, used = 1;
+    std::vector<int32_t> deps;
+    for (int j = 0; j < n; j++) {
+        Op& op = list[j];
+        if (op.kind != OP_GENERIC && op.kind != OP_GEMM) {  // barrier: joins everything, runs on branch 0
+            barrier = j;
+            recs.clear();
+            last_ws = -1;
+            for (int b = 0; b < B; b++) { tail[b] = -1; is_free[b] = 1; }
+            tail[0] = j;
+            continue;
+        }
+        deps.clear();
+        const int pa = producer(op.a), pb = producer(op.b);
+        if (pa > barrier) deps.push_back(pa);
+        if (pb > barrier) deps.push_back(pb);
+        const int64_t lo = op.c_offset, hi = op.c_offset + ((int64_t)1 << (op.m + op.n));
+        size_t keep = 0;
+        for (size_t r = 0; r < recs.size(); r++) {
+            const Rec& R = recs[r];
+            const bool overlap = R.lo < hi && lo < R.hi;
+            if (overlap) deps.push_back(R.op);
+            if (!(overlap && R.lo >= lo && R.hi <= hi)) recs[keep++] = R;  // fully overwritten records are superseded
+        }
+        recs.resize(keep);
+        if (op.ksplit_log2 > 0) {
+            if (last_ws > barrier) deps.push_back(last_ws);
+            last_ws = j;
+        }
+        // branch: directly behind a producer whose branch has not moved on, else a free one, else the stalest
+        int br = -1;
+        for (int pi : {pa, pb})
+            if (br < 0 && pi > barrier && tail[list[pi].branch] == pi) br = list[pi].branch;
+        // a stream never used since the barrier first: behind a finished chain the new one would inherit that
+        // chain's stream order (a false dependency, also in the captured graph); then the free stream whose
+        // tail is oldest
+        if (br < 0)
+            for (int b = 0; b < B && br < 0; b++)
+                if (is_free[b] && tail[b] < 0) br = b;
+        if (br < 0)
+            for (int b = 0; b < B; b++)
+                if (is_free[b] && (br < 0 || tail[b] < tail[br])) br = b;
+        if (br < 0) {
+            br = 0;
+            for (int b = 1; b < B; b++)
+                if (tail[b] < tail[br]) br = b;
+        }
+        op.branch = br;
+        used = std::max(used, br + 1);
+        for (int pi : {pa, pb})
+            if (pi > barrier && list[pi].branch != br && tail[list[pi].branch] == pi) is_free[list[pi].branch] = 1;
+        tail[br] = j;
+        is_free[br] = consumer[j] < 0 ? 1 : 0;
+        std::sort(deps.begin(), deps.end());
+        deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+        for (int i : deps) {
+            const int bi = list[i].branch;
+            if (bi == br || i <= waited[br][bi]) continue;  // stream order / an earlier wait already covers it
+            op.waits.push_back(i);
+            list[i].signal = 1;
+            waited[br][bi] = i;
+        }
+        for (const OperandRef* r : {&op.a, &op.b})
+            if (r->space != 0) {
+                const int rank = (r == &op.a ? op.m : op.n) + op.k;
+                recs.push_back(Rec{r->offset, r->offset + ((int64_t)1 << rank), j});
+            }
+        recs.push_back(Rec{lo, hi, j});
+    }
+    return used;
+}
 
 static bool contains(const std::vector<int32_t>& sorted, int32_t e) {
     return std::binary_search(sorted.begin(), sorted.end(), e);
@@ -271,6 +408,8 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
 
     // ---- ops (post-order), micro subtrees, hoisting, arena ----
     const bool hoist = opt.hoist_invariant && S > 0;
+    const int max_branches = opt.dag_branches == 0 ? 16 : opt.dag_branches;
+    const bool dag = max_branches > 1;
     Arena arena;
     int64_t ws_max = 0;
     std::vector<int64_t> size_of(N, 0);
@@ -334,7 +473,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     auto place = [&](Op& op, int i) {
         NodeInfo& X = P->nodes[i];
         size_of[i] = (int64_t)1 << (op.m + op.n);
-        op.c_offset = arena.alloc(size_of[i]);
+        op.c_offset = arena.alloc(size_of[i], i - subtree_nodes[i] + 1, i, dag);
         X.where.space = persistent[i] ? 2 : 1;  // hoisted results are read by every lane from lane 0's arena
         X.where.offset = op.c_offset;
         X.where.leaf = -1;
@@ -354,13 +493,14 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         }
         for (int c : {X.left, X.right}) {
             const NodeInfo& Cn = P->nodes[c];
-            if (Cn.leaf < 0 && !persistent[c]) arena.release(Cn.where.offset, size_of[c]);
+            if (Cn.leaf < 0 && !persistent[c]) arena.release(Cn.where.offset, size_of[c], i);
         }
         list->push_back(op);
     };
     auto run_phase = [&](int dep, std::vector<Op>* list, int which) {
         // 1. all micro subtrees of this phase: one launch, one CTA per (packed) subtree
         MicroProgram& mp = P->micro[which];
+        arena.barrier();  // a new phase starts after everything before it has finished
         std::vector<std::vector<Op>> subtrees;
         std::vector<double> work;
         std::vector<std::pair<int64_t, int64_t>> deferred;  // arena space freed only after the launch
@@ -415,6 +555,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             list->push_back(launch);
             for (auto& d : deferred) arena.release(d.first, d.second);
         }
+        arena.barrier();  // the micro launch (or the phase start) orders everything released so far
         // 2. the other joins of this phase, post-order
         for (int i = 0; i < N; i++)
             if (P->nodes[i].leaf < 0 && !closed[i] && eff_dep[i] == dep) emit(i, list);
@@ -439,6 +580,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     const int want_lanes = opt.slice_lanes;
     const bool cheap = (P->arena_doubles + P->ws_doubles) * 8 <= ((int64_t)2 << 30);
     P->lanes = (S > 0 && (want_lanes == 2 || (want_lanes == 0 && cheap))) ? 2 : 1;
+    P->branches = std::max(schedule_branches(&P->invariant_ops, max_branches), schedule_branches(&P->slice_ops, max_branches));
     return TOB_OK;
 }
 
@@ -471,11 +613,14 @@ std::string describe(const Program& P) {
             o << ",\"c_offset\":" << op.c_offset << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
               << ",\"mask_m\":" << op.mask_m << ",\"threads_per_out\":" << op.threads_per_out
               << ",\"ksplit_log2\":" << op.ksplit_log2 << ",\"tm_log2\":" << op.tm_log2 << ",\"tn_log2\":" << op.tn_log2
-              << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops << ",\"bytes\":" << op.bytes << "}";
+              << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops << ",\"bytes\":" << op.bytes
+              << ",\"branch\":" << op.branch << ",\"signal\":" << op.signal << ",\"waits\":[";
+            for (size_t w = 0; w < op.waits.size(); w++) o << (w ? "," : "") << op.waits[w];
+            o << "]}";
         }
         o << "]";
     };
-    o << "{\"n_slice_groups\":" << P.n_slice_groups << ",\"lanes\":" << P.lanes << ",\"leaf_doubles\":" << P.leaf_doubles
+    o << "{\"n_slice_groups\":" << P.n_slice_groups << ",\"lanes\":" << P.lanes << ",\"branches\":" << P.branches << ",\"leaf_doubles\":" << P.leaf_doubles
       << ",\"arena_doubles\":" << P.arena_doubles << ",\"ws_doubles\":" << P.ws_doubles
       << ",\"total_flops\":" << P.total_flops << ",\"total_bytes\":" << P.total_bytes << ",\"leaves\":[";
     for (size_t l = 0; l < P.leaves.size(); l++) {

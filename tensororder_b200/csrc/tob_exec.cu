@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@ using namespace tob;
 
 constexpr int kMaxLanes = 2;        // slices in flight at once (each lane: own arena, workspace, stream)
 constexpr int kMaxResults = 4096;   // per-slice results buffered on the device before the ordered sum
+constexpr int kMaxBranches = 32;    // streams per lane for the DAG schedule (Op::branch); branch 0 is the lane's stream
 
 struct Lane {
     cudaStream_t stream = nullptr;  // lane 0: the plan's stream (own or caller's); lane >= 1: own stream
@@ -40,6 +42,15 @@ struct Lane {
     DevState* d_state = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t inv_graph = nullptr;          // lane 0: the slice-invariant prologue as a graph (reused plans)
+    cudaGraphExec_t inv_graph_exec = nullptr;
+    // DAG schedule: branch b >= 1 runs on branch_stream[b]; branch_ev[b] joins it back, ev_fork releases it
+    int n_branches = 1;
+    cudaStream_t branch_stream[kMaxBranches] = {nullptr};
+    cudaEvent_t branch_ev[kMaxBranches] = {nullptr};
+    cudaEvent_t branch_ev_spare[kMaxBranches] = {nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> op_ev[2];        // [list][op index]: recorded after ops other branches wait for
 };
 
 struct tob_plan {
@@ -67,13 +78,13 @@ struct tob_plan {
     bool has_terms = false;
     double last_ms = 0;
     int64_t last_launches = 0;
-    int64_t graph_launches_per_slice = 0;
+    int64_t graph_launches_per_slice = 0, inv_graph_launches = 0;
     int64_t runs = 0;
     std::vector<cudaEvent_t> gemm_events;  // pairs
     std::vector<double> gemm_event_flops;
     double last_gemm_ms = 0, last_gemm_flops = 0;
     int64_t last_gemm_launches = 0;
-    double slice_flops = 0;
+    double slice_flops = 0, invariant_flops = 0;
     bool time_gemm = false;
     double modulus = 0.0;  // exact mode: prime modulus (< 2^23), 0 = float64 arithmetic
 };
@@ -205,6 +216,26 @@ void streams_release(const StreamSet& s) {
     g_free_streams.push_back(s);
 }
 
+// ordering-only events (no timing) for the DAG schedule, recycled per device
+std::vector<std::pair<int, cudaEvent_t>> g_free_events;
+cudaError_t event_acquire(int device, cudaEvent_t* out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (size_t i = g_free_events.size(); i-- > 0;)
+            if (g_free_events[i].first == device) {
+                *out = g_free_events[i].second;
+                g_free_events.erase(g_free_events.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    return cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+}
+void event_release(int device, cudaEvent_t e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    g_free_events.emplace_back(device, e);
+}
+
 }  // namespace
 
 static int ensure_device(int device) {
@@ -236,6 +267,7 @@ void tob_default_options(tob_options* opt) {
     opt->mem_limit_bytes = 0;
     opt->use_microtree = 1;
     opt->slice_lanes = 0;
+    opt->dag_branches = 0;
 }
 
 const char* tob_last_error(void) { return g_error.c_str(); }
@@ -286,15 +318,28 @@ int64_t tob_plan_describe(const tob_plan* p, char* buf, int64_t cap) {
 
 int64_t tob_plan_num_ops(const tob_plan* p) { return (int64_t)(p->prog.invariant_ops.size() + p->prog.slice_ops.size()); }
 
-static void release_device(tob_plan* p) {
+static void release_lanes(tob_plan* p) {
     for (int l = 0; l < kMaxLanes; l++) {
         Lane& L = p->lane[l];
         if (L.own_stream) cudaStreamSynchronize(L.own_stream);
+        for (int b = 1; b < L.n_branches; b++)
+            if (L.branch_stream[b]) cudaStreamSynchronize(L.branch_stream[b]);
         if (L.graph_exec) cudaGraphExecDestroy(L.graph_exec);
         if (L.graph) cudaGraphDestroy(L.graph);
+        if (L.inv_graph_exec) cudaGraphExecDestroy(L.inv_graph_exec);
+        if (L.inv_graph) cudaGraphDestroy(L.inv_graph);
         if (L.own_stream) streams_release(StreamSet{L.own_stream, L.ev_a, L.ev_b, p->device});
+        for (int b = 1; b < L.n_branches; b++)
+            if (L.branch_stream[b]) streams_release(StreamSet{L.branch_stream[b], L.branch_ev[b], L.branch_ev_spare[b], p->device});
+        event_release(p->device, L.ev_fork);
+        for (int w = 0; w < 2; w++)
+            for (cudaEvent_t e : L.op_ev[w]) event_release(p->device, e);
         L = Lane();
     }
+}
+
+static void release_device(tob_plan* p) {
+    release_lanes(p);
     pool_release(Block{p->d_block, p->d_block_size, p->device, false});
     pool_release(Block{p->h_block, p->h_block_size, p->device, true});
     for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
@@ -345,8 +390,31 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         p->lane[l].ev_a = ss.ev0;
         p->lane[l].ev_b = ss.ev1;
     }
+    // DAG schedule: branch streams + one ordering event per op another branch waits for
+    for (int l = 0; l < p->n_lanes; l++) {
+        Lane& Ln = p->lane[l];
+        Ln.n_branches = std::min<int>(std::max<int>(G.branches, 1), kMaxBranches);
+        if (Ln.n_branches > 1) CUDA_TRY(event_acquire(p->device, &Ln.ev_fork));
+        for (int b = 1; b < Ln.n_branches; b++) {
+            StreamSet ss;
+            CUDA_TRY(streams_acquire(p->device, &ss));
+            Ln.branch_stream[b] = ss.stream;
+            Ln.branch_ev[b] = ss.ev0;
+            Ln.branch_ev_spare[b] = ss.ev1;
+        }
+        for (int w = 0; w < 2; w++) {
+            const std::vector<Op>& list = w ? G.slice_ops : G.invariant_ops;
+            if (w == 0 && l > 0) break;  // the invariant prologue runs on lane 0 only
+            Ln.op_ev[w].assign(list.size(), nullptr);
+            if (Ln.n_branches > 1)
+                for (size_t j = 0; j < list.size(); j++)
+                    if (list[j].signal) CUDA_TRY(event_acquire(p->device, &Ln.op_ev[w][j]));
+        }
+    }
     p->slice_flops = 0;
     for (const Op& op : G.slice_ops) p->slice_flops += op.flops;
+    p->invariant_flops = 0;
+    for (const Op& op : G.invariant_ops) p->invariant_flops += op.flops;
 
     // ---- host-side tables ----
     const int L = (int)G.leaves.size();
@@ -395,10 +463,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             set_error("plan needs " + std::to_string(total_bytes) + " bytes, device has " + std::to_string(free_b) + " free");
-            for (int l = 0; l < p->n_lanes; l++) {
-                streams_release(StreamSet{p->lane[l].own_stream, p->lane[l].ev_a, p->lane[l].ev_b, p->device});
-                p->lane[l] = Lane();
-            }
+            release_lanes(p);
             return TOB_E_OOM;
         }
         CUDA_TRY(e);
@@ -527,10 +592,11 @@ static KParams make_params(const tob_plan* p, const Lane& L, const Op& op) {
     return k;
 }
 
-static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* launches) {
+static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* launches, cudaStream_t stream = nullptr) {
+    if (!stream) stream = L.stream;
     if (op.kind == OP_ACCUM) {
         (*launches)++;
-        return launch_accum(L.d_state, operand_ptr(p, L, op.a), L.d_leaf_off, op.a.leaf, p->d_results, L.stream);
+        return launch_accum(L.d_state, operand_ptr(p, L, op.a), L.d_leaf_off, op.a.leaf, p->d_results, stream);
     }
     if (op.kind == OP_MICRO) {
         const int w = op.micro_which;
@@ -540,10 +606,52 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
         for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
         const int smem_ops = std::min(max_ops, (int)(64 * 1024 / sizeof(MicroOpDev)));
         return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops,
-                                p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, p->modulus, L.stream);
+                                p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, p->modulus, stream);
     }
     KParams k = make_params(p, L, op);
-    return launch_contract(op, k, L.stream, launches);
+    return launch_contract(op, k, stream, launches);
+}
+
+// Issues one op list along its DAG schedule (Op::branch / waits / signal, tob_compile.cpp).  Works the same
+// under stream capture: the event records and waits become the graph's dependency edges.
+static cudaError_t run_list(tob_plan* p, Lane& L, const std::vector<Op>& list, int which,
+                            const std::function<cudaError_t(const Op&, cudaStream_t)>& launch) {
+    cudaError_t e = cudaSuccess;
+    const bool multi = L.n_branches > 1;
+    bool forked[kMaxBranches] = {false}, dirty[kMaxBranches] = {false};
+    auto join_all = [&]() -> cudaError_t {
+        for (int b = 1; b < L.n_branches; b++) {
+            if (!dirty[b]) { forked[b] = false; continue; }
+            cudaError_t e2 = cudaEventRecord(L.branch_ev[b], L.branch_stream[b]);
+            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(L.stream, L.branch_ev[b], 0);
+            if (e2 != cudaSuccess) return e2;
+            dirty[b] = forked[b] = false;
+        }
+        return cudaSuccess;
+    };
+    if (multi && (e = cudaEventRecord(L.ev_fork, L.stream)) != cudaSuccess) return e;
+    for (size_t j = 0; j < list.size(); j++) {
+        const Op& op = list[j];
+        if (op.kind != OP_GENERIC && op.kind != OP_GEMM) {  // barrier ops run on the lane's stream after a full join
+            if ((e = join_all()) != cudaSuccess) return e;
+            if ((e = launch(op, L.stream)) != cudaSuccess) return e;
+            if (multi && (e = cudaEventRecord(L.ev_fork, L.stream)) != cudaSuccess) return e;
+            continue;
+        }
+        const int b = multi ? std::min<int>(op.branch, L.n_branches - 1) : 0;
+        cudaStream_t s = b ? L.branch_stream[b] : L.stream;
+        if (b && !forked[b]) {
+            if ((e = cudaStreamWaitEvent(s, L.ev_fork, 0)) != cudaSuccess) return e;
+            forked[b] = true;
+        }
+        if (multi)
+            for (int32_t w : op.waits)
+                if ((e = cudaStreamWaitEvent(s, L.op_ev[which][w], 0)) != cudaSuccess) return e;
+        if ((e = launch(op, s)) != cudaSuccess) return e;
+        if (multi && op.signal && (e = cudaEventRecord(L.op_ev[which][j], s)) != cudaSuccess) return e;
+        if (b) dirty[b] = true;
+    }
+    return join_all();
 }
 
 static cudaError_t launch_begin(tob_plan* p, const Lane& L, int* launches) {
@@ -553,14 +661,11 @@ static cudaError_t launch_begin(tob_plan* p, const Lane& L, int* launches) {
     return launch_begin_slice(L.d_state, t, L.stream);
 }
 
-static cudaError_t launch_slice(tob_plan* p, const Lane& L, int* launches) {
+static cudaError_t launch_slice(tob_plan* p, Lane& L, int* launches) {
     cudaError_t e = launch_begin(p, L, launches);
     if (e != cudaSuccess) return e;
-    for (const Op& op : p->prog.slice_ops) {
-        e = launch_op(p, L, op, launches);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+    return run_list(p, L, p->prog.slice_ops, 1,
+                    [&](const Op& op, cudaStream_t s) { return launch_op(p, L, op, launches, s); });
 }
 
 int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double* result) {
@@ -587,34 +692,38 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     const bool skip_invariant = (flags & TOB_RUN_SKIP_INVARIANT) != 0 && p->runs > 0;
     size_t n_gemm = 0;
     cudaEvent_t last_gemm_end = nullptr;
-    const Lane* last_gemm_lane = nullptr;
+    cudaStream_t last_gemm_stream = nullptr;
     // plain stream launches: bracket every DMMA GEMM with CUDA events (per-kernel roofline, bench.py).
-    // GEMMs of different lanes are chained (a GEMM waits for the previous GEMM of the other lane): two
-    // tensor-pipe-bound kernels gain nothing from sharing the SMs, and each event pair then brackets one
-    // GEMM running alone with only the other lane's small kernels beside it.
-    auto timed_op = [&](const Lane& L, const Op& op) -> int {
-        if (op.kind != OP_GEMM || as_graph || !p->time_gemm) {
-            CUDA_TRY(launch_op(p, L, op, &launches));
-            return TOB_OK;
-        }
+    // GEMMs on different streams (lanes, DAG branches) are chained (a GEMM waits for the previous GEMM):
+    // two tensor-pipe-bound kernels gain nothing from sharing the SMs, and each event pair then brackets
+    // one GEMM running alone with only small kernels of other streams beside it.
+    auto timed_op = [&](const Lane& L, const Op& op, cudaStream_t s) -> cudaError_t {
+        if (op.kind != OP_GEMM || !p->time_gemm) return launch_op(p, L, op, &launches, s);
+        cudaError_t e = cudaSuccess;
         if (p->gemm_events.size() < 2 * (n_gemm + 1)) {
             cudaEvent_t a, b;
-            CUDA_TRY(cudaEventCreate(&a));
-            CUDA_TRY(cudaEventCreate(&b));
+            if ((e = cudaEventCreate(&a)) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&b)) != cudaSuccess) return e;
             p->gemm_events.push_back(a);
             p->gemm_events.push_back(b);
             p->gemm_event_flops.push_back(0.0);
         }
-        if (last_gemm_end && last_gemm_lane != &L) CUDA_TRY(cudaStreamWaitEvent(L.stream, last_gemm_end, 0));
-        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm], L.stream));
-        CUDA_TRY(launch_op(p, L, op, &launches));
-        CUDA_TRY(cudaEventRecord(p->gemm_events[2 * n_gemm + 1], L.stream));
+        if (last_gemm_end && last_gemm_stream != s && (e = cudaStreamWaitEvent(s, last_gemm_end, 0)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p->gemm_events[2 * n_gemm], s)) != cudaSuccess) return e;
+        if ((e = launch_op(p, L, op, &launches, s)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p->gemm_events[2 * n_gemm + 1], s)) != cudaSuccess) return e;
         last_gemm_end = p->gemm_events[2 * n_gemm + 1];
-        last_gemm_lane = &L;
+        last_gemm_stream = s;
         p->gemm_event_flops[n_gemm] = op.flops;
         n_gemm++;
-        return TOB_OK;
+        return cudaSuccess;
     };
+    // the slice-invariant prologue replays as a graph too once the plan is reused and it is launch-bound
+    // (its GEMMs then go untimed, so not while per-GEMM timing wants them)
+    bool inv_has_gemm = false;
+    for (const Op& op : p->prog.invariant_ops) inv_has_gemm |= (op.kind == OP_GEMM);
+    const bool inv_as_graph = (ug == 1 || (ug == 2 && p->invariant_flops < 2e9 && p->runs > 0)) &&
+                              !(p->time_gemm && inv_has_gemm) && !p->prog.invariant_ops.empty();
 
     CUDA_TRY(cudaEventRecord(L0.ev_a, L0.stream));
     uint64_t done = 0;
@@ -630,11 +739,26 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
             p->h_state[l].slot_stride = lanes;
         }
         CUDA_TRY(cudaMemcpyAsync(L0.d_state, p->h_state, sizeof(DevState) * lanes, cudaMemcpyHostToDevice, L0.stream));
-        if (first_batch && batch > 0 && !skip_invariant)
-            for (const Op& op : p->prog.invariant_ops) {
-                int rc2 = timed_op(L0, op);
-                if (rc2 != TOB_OK) return rc2;
+        if (first_batch && batch > 0 && !skip_invariant) {
+            if (inv_as_graph) {
+                if (!L0.inv_graph_exec) {
+                    int n_inv = 0;
+                    CUDA_TRY(cudaStreamBeginCapture(L0.stream, cudaStreamCaptureModeThreadLocal));
+                    cudaError_t e = run_list(p, L0, p->prog.invariant_ops, 0,
+                                             [&](const Op& op, cudaStream_t s) { return launch_op(p, L0, op, &n_inv, s); });
+                    cudaError_t e2 = cudaStreamEndCapture(L0.stream, &L0.inv_graph);
+                    CUDA_TRY(e);
+                    CUDA_TRY(e2);
+                    CUDA_TRY(cudaGraphInstantiate(&L0.inv_graph_exec, L0.inv_graph, 0));
+                    p->inv_graph_launches = n_inv;
+                }
+                CUDA_TRY(cudaGraphLaunch(L0.inv_graph_exec, L0.stream));
+                launches += (int)p->inv_graph_launches;
+            } else {
+                CUDA_TRY(run_list(p, L0, p->prog.invariant_ops, 0,
+                                  [&](const Op& op, cudaStream_t s) { return timed_op(L0, op, s); }));
             }
+        }
         // fork: the other lanes start after the state upload and the slice-invariant prologue
         for (int l = 1; l < lanes; l++) {
             CUDA_TRY(cudaEventRecord(p->lane[l].ev_a, L0.stream));
@@ -657,12 +781,10 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
             launches += (int)(p->graph_launches_per_slice * batch);
         } else {
             for (uint64_t j = 0; j < batch; j++) {
-                const Lane& L = p->lane[j % lanes];
+                Lane& L = p->lane[j % lanes];
                 CUDA_TRY(launch_begin(p, L, &launches));
-                for (const Op& op : p->prog.slice_ops) {
-                    int rc2 = timed_op(L, op);
-                    if (rc2 != TOB_OK) return rc2;
-                }
+                CUDA_TRY(run_list(p, L, p->prog.slice_ops, 1,
+                                  [&](const Op& op, cudaStream_t s) { return timed_op(L, op, s); }));
             }
         }
         // join, then the ordered sum of this batch's per-slice results (sequential, slice order)
@@ -725,6 +847,8 @@ int tob_plan_set_stream(tob_plan* p, void* stream) {
     Lane& L0 = p->lane[0];
     if (L0.graph_exec) { cudaGraphExecDestroy(L0.graph_exec); L0.graph_exec = nullptr; }
     if (L0.graph) { cudaGraphDestroy(L0.graph); L0.graph = nullptr; }
+    if (L0.inv_graph_exec) { cudaGraphExecDestroy(L0.inv_graph_exec); L0.inv_graph_exec = nullptr; }
+    if (L0.inv_graph) { cudaGraphDestroy(L0.inv_graph); L0.inv_graph = nullptr; }
     L0.stream = stream ? (cudaStream_t)stream : L0.own_stream;
     return TOB_OK;
 }

@@ -45,6 +45,12 @@ struct Op {
     int32_t invariant = 0;      // 1: independent of the slice id (hoisted)
     int32_t micro_which = -1;   // OP_MICRO: index into Program::micro
     double flops = 0, bytes = 0;
+    // DAG schedule inside the op's list (schedule_branches): ops of one branch run in list order on one
+    // stream; `waits` names ops of OTHER branches (list indices) that must have finished first — the
+    // producers of the operands and the last users of the arena space the result overwrites.
+    int32_t branch = 0;
+    int32_t signal = 0;           // 1: an op of another branch waits for this one (record an event)
+    std::vector<int32_t> waits;
 };
 
 // Tiny subtrees (every operand and result <= 2^12 doubles, <= 2^15 multiply-adds per join, closed under
@@ -88,6 +94,7 @@ struct Program {
     int64_t arena_doubles = 0;        // intermediates
     int64_t ws_doubles = 0;           // split-K workspace
     int32_t lanes = 1;                // slices in flight at once (each lane has its own arena + workspace)
+    int32_t branches = 1;             // streams per lane used by the DAG schedule of the op lists
     int64_t src_leaf_len = 0;
     double total_flops = 0, total_bytes = 0;
     OperandRef root;                  // rank-0 result of one slice
@@ -98,6 +105,9 @@ std::string describe(const Program& p);
 
 // Shared by compile and the stand-alone tensordot: pick kernel + configuration for a canonical join.
 void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk);
+
+// Assigns Op::branch / waits / signal for one op list; returns the number of branches used.
+int schedule_branches(std::vector<Op>* list, int max_branches);
 
 void set_error(const std::string& msg);
 

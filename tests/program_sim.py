@@ -42,8 +42,49 @@ def upload_leaves(desc, flat):
     return dev
 
 
-def run_program(desc, flat, first=0, count=None, stride=1, modulus=0):
-    """modulus > 0: the exact mode — every op reduces modulo the prime (done here in int64, exact)."""
+def dag_order(ops, rng):
+    """A random order of one op list that respects ONLY what the executor enforces (tob_exec.cu run_list):
+    list order inside a branch, the declared cross-branch waits, and the barrier ops (micro launch,
+    accumulate) that join every branch.  If the compiler's dependency analysis misses a hazard, some
+    seed reorders the two ops and the result changes."""
+    n = len(ops)
+    preds = [set() for _ in range(n)]
+    last_on_branch = {}
+    barrier = None
+    since_barrier = []
+    for j, op in enumerate(ops):
+        if op["kind"] in (2, 3):  # barrier
+            preds[j].update(since_barrier)
+            if barrier is not None:
+                preds[j].add(barrier)
+            barrier, since_barrier, last_on_branch = j, [], {}
+            continue
+        if barrier is not None:
+            preds[j].add(barrier)
+        b = op.get("branch", 0)
+        if b in last_on_branch:
+            preds[j].add(last_on_branch[b])
+        last_on_branch[b] = j
+        for w in op.get("waits", []):
+            assert w < j and ops[w].get("signal") == 1 and ops[w].get("branch", 0) != b
+            preds[j].add(w)
+        since_barrier.append(j)
+    done, order = set(), []
+    ready = [j for j in range(n) if not preds[j]]
+    while ready:
+        j = ready.pop(int(rng.integers(len(ready))))
+        order.append(j)
+        done.add(j)
+        for q in range(n):
+            if q not in done and q not in ready and preds[q] <= done:
+                ready.append(q)
+    assert len(order) == n
+    return order
+
+
+def run_program(desc, flat, first=0, count=None, stride=1, modulus=0, dag_seed=None):
+    """modulus > 0: the exact mode — every op reduces modulo the prime (done here in int64, exact).
+    dag_seed: execute every op list in a random order allowed by its DAG schedule instead of list order."""
     S = desc["n_slice_groups"]
     if count is None:
         count = ((1 << S) - first + stride - 1) // stride
@@ -92,8 +133,13 @@ def run_program(desc, flat, first=0, count=None, stride=1, modulus=0):
         invariant_nodes.add(op.get("node"))
         for sub in op.get("micro", []):
             invariant_nodes.add(sub["node"])
-    for op in desc["invariant_ops"]:
-        do(op)
+    rng = np.random.default_rng(dag_seed) if dag_seed is not None else None
+
+    def run_list(ops):
+        for j in (dag_order(ops, rng) if rng is not None else range(len(ops))):
+            do(ops[j])
+
+    run_list(desc["invariant_ops"])
     sid = first
     for _ in range(count):
         for l, L in enumerate(desc["leaves"]):
@@ -101,7 +147,6 @@ def run_program(desc, flat, first=0, count=None, stride=1, modulus=0):
             for ib, ab in zip(L["slice_id_bit"], L["slice_addr_bit"]):
                 off |= ((sid >> ib) & 1) << ab
             leaf_off[l] = off
-        for op in desc["slice_ops"]:
-            do(op)
+        run_list(desc["slice_ops"])
         sid += stride
     return acc

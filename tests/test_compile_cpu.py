@@ -122,6 +122,56 @@ def test_micro_subtrees(name, variant):
     assert math.isclose(a, b, rel_tol=1e-12) and math.isclose(a, pp.expected["count"], rel_tol=1e-12)
 
 
+def _dag_cases():
+    return [("vc50_lineflow", None), ("vc100_lineflow", None), ("vc100_lineflow", "min4"), ("vc150_lineflow", None),
+            ("vc150_lineflow", "min4"), ("vc150_mcc_factorflow", "min3"), ("rand3cnf_24_lineflow", None),
+            ("rand3cnf_24_lineflow", "min3"), ("rand4cnf_18_mcc_lineflow", "min2"), ("vc100_mcc_factorflow", None)]
+
+
+@pytest.mark.parametrize("name,variant", _dag_cases())
+def test_dag_schedule_orders_every_hazard(name, variant):
+    """Joins of independent subtrees run concurrently on several streams (Op::branch / waits).  The
+    simulator executes the ops in random orders that respect only the declared schedule, against ONE
+    shared arena: a missing RAW / WAR / WAW edge changes the result (or reads NaN-poisoned space)."""
+    pp = load_golden(name)
+    if variant:
+        pp = pp.variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    want = pp.expected.get("count", load_golden(name).expected["count"])
+    for branches in (0, 3, 32):
+        for microtree in (True, False):
+            cp = CompiledPlan(flat, dag_branches=branches, use_microtree=microtree)
+            desc = cp.describe()
+            ops = desc["invariant_ops"] + desc["slice_ops"]
+            used = 1 + max(op.get("branch", 0) for op in ops)
+            assert used == desc["branches"] <= (16 if branches == 0 else branches)
+            seq = run_program(desc, flat)
+            assert math.isclose(seq, want, rel_tol=1e-12)
+            for seed in range(4):
+                got = run_program(desc, flat, dag_seed=seed)
+                assert got == seq or math.isclose(got, seq, rel_tol=1e-13), (branches, microtree, seed, got, seq)
+            cp.close()
+    one = CompiledPlan(flat, dag_branches=1).describe()
+    assert one["branches"] == 1 and all(not op.get("waits") for op in one["invariant_ops"] + one["slice_ops"])
+    # the point of the schedule: the longest chain is far shorter than the op count
+    if name == "vc150_lineflow" and variant is None:
+        desc = CompiledPlan(flat).describe()
+        ops = desc["slice_ops"]
+        depth = [0] * len(ops)
+        last = {}
+        for j, op in enumerate(ops):
+            if op["kind"] in (2, 3):
+                depth[j] = 1 + max(depth[:j], default=0)
+                last = {}
+                continue
+            b = op["branch"]
+            d = max([depth[w] for w in op["waits"]] + [depth[last[b]] if b in last else 0] +
+                    [depth[i] for i in range(j) if ops[i]["kind"] in (2, 3)])
+            depth[j] = d + 1
+            last[b] = j
+        assert max(depth) < len(ops) // 2, (max(depth), len(ops))
+
+
 def test_plan_errors():
     pp = load_golden("toy_path_lineflow")
     plan = pp.as_execution_plan()

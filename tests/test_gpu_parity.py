@@ -97,6 +97,39 @@ def test_hoisting_does_not_change_result():
     _check(a, pp.expected)
 
 
+@pytest.mark.parametrize("name,variant", [("vc100_lineflow", None), ("vc150_lineflow", None), ("vc150_lineflow", "min4"),
+                                          ("vc190_lineflow", None), ("vc200_lineflow", "min3"),
+                                          ("vc150_mcc_factorflow", "min3"), ("rand3cnf_24_lineflow", "min3"),
+                                          ("rand4cnf_18_mcc_lineflow", None)])
+def test_dag_schedule_is_bit_identical_to_post_order(name, variant):
+    """Independent subtrees run concurrently on up to 16 streams per lane (fork/join by events, captured as a
+    DAG when the slice replays as a graph).  Every join computes the same sums in the same order whatever
+    runs beside it, so the count equals the one-stream post-order run bit for bit — in stream mode, as
+    graphs, on the first run and on replays of a resident plan."""
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name)
+    if variant:
+        pp = pp.variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    results = {}
+    for branches in (1, 0, 3, 32):
+        for graph in (0, 1, 2):
+            cp = CompiledPlan(flat, dag_branches=branches, use_graph=graph)
+            cp.upload()
+            got = [cp.run() for _ in range(3)]
+            assert got[0] == got[1] == got[2], (branches, graph, got)
+            results[(branches, graph)] = got[0]
+            if branches != 1:
+                assert cp.describe()["branches"] > 1
+            cp.close()
+    assert len(set(results.values())) == 1, results
+    want = pp.expected.get("count", load_golden(name).expected.get("count"))
+    if want is not None:
+        assert math.isclose(results[(0, 2)], want, rel_tol=REL)
+
+
 @pytest.mark.parametrize("name", [n for n in ALL if "count" not in load_golden(n).expected])
 def test_large_instances_slicing_invariance(name):
     """No reference count is stored for the largest family members (numpy needs minutes and tens of
