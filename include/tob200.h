@@ -116,6 +116,10 @@ int tob_plan_run_ex(tob_plan* plan, uint64_t first, uint64_t count, uint64_t str
 /* Device time (CUDA events on the plan's stream) of the last tob_plan_run, in milliseconds. */
 double tob_plan_last_ms(const tob_plan* plan);
 
+/* Host time (ms) the last tob_plan_run spent issuing work, i.e. before it started waiting for the device:
+ * tells a launch-bound run that is limited by the host's launch rate from one limited by the device. */
+double tob_plan_last_issue_ms(const tob_plan* plan);
+
 /* Number of kernels launched by the last tob_plan_run. */
 int64_t tob_plan_last_launches(const tob_plan* plan);
 

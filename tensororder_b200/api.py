@@ -172,6 +172,10 @@ class CompiledPlan:
         return float(cabi.lib.tob_plan_last_ms(self._handle))
 
     @property
+    def last_issue_ms(self) -> float:
+        return float(cabi.lib.tob_plan_last_issue_ms(self._handle))
+
+    @property
     def last_launches(self) -> int:
         return int(cabi.lib.tob_plan_last_launches(self._handle))
 

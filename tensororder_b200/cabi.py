@@ -53,6 +53,7 @@ SYMBOLS = {
     "tob_plan_run": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_double)]),
     "tob_plan_run_ex": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, c_double, c_int32, POINTER(c_double)]),
     "tob_plan_last_ms": (c_double, [c_void_p]),
+    "tob_plan_last_issue_ms": (c_double, [c_void_p]),
     "tob_plan_last_launches": (c_int64, [c_void_p]),
     "tob_plan_set_modulus": (c_int32, [c_void_p, c_double]),
     "tob_plan_set_gemm_timing": (c_int32, [c_void_p, c_int32]),

@@ -184,13 +184,14 @@ int schedule_branches(std::vector<Op>* list_p, int max_branches) {
     for (Op& op : list) { op.branch = 0; op.signal = 0; op.waits.clear(); }
     if (max_branches <= 1 || n < 3) return 1;
     const int B = std::min(max_branches, 32);
-    std::map<int32_t, int32_t> idx_of_node;
+    int32_t max_node = 0;
+    for (const Op& op : list) max_node = std::max(max_node, op.node);
+    std::vector<int32_t> idx_of_node((size_t)max_node + 1, -1);
     for (int j = 0; j < n; j++)
         if (list[j].kind == OP_GENERIC || list[j].kind == OP_GEMM) idx_of_node[list[j].node] = j;
     auto producer = [&](const OperandRef& r) -> int {
-        if (r.space == 0) return -1;
-        auto it = idx_of_node.find(r.node);
-        return it == idx_of_node.end() ? -1 : it->second;
+        if (r.space == 0 || r.node < 0 || r.node > max_node) return -1;
+        return idx_of_node[r.node];
     };
     std::vector<int32_t> consumer(n, -1);
     for (int j = 0; j < n; j++) {

@@ -76,7 +76,7 @@ struct tob_plan {
     DevState* h_state = nullptr;   // upload slots, one per lane
     double* h_readback = nullptr;  // result slot
     bool has_terms = false;
-    double last_ms = 0;
+    double last_ms = 0, last_issue_ms = 0;
     int64_t last_launches = 0;
     int64_t graph_launches_per_slice = 0, inv_graph_launches = 0;
     int64_t runs = 0;
@@ -404,7 +404,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         }
         for (int w = 0; w < 2; w++) {
             const std::vector<Op>& list = w ? G.slice_ops : G.invariant_ops;
-            if (w == 0 && l > 0) break;  // the invariant prologue runs on lane 0 only
+            if (w == 0 && l > 0) continue;  // the invariant prologue runs on lane 0 only
             Ln.op_ev[w].assign(list.size(), nullptr);
             if (Ln.n_branches > 1)
                 for (size_t j = 0; j < list.size(); j++)
@@ -725,6 +725,7 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     const bool inv_as_graph = (ug == 1 || (ug == 2 && p->invariant_flops < 2e9 && p->runs > 0)) &&
                               !(p->time_gemm && inv_has_gemm) && !p->prog.invariant_ops.empty();
 
+    const double t_issue0 = now_ms();
     CUDA_TRY(cudaEventRecord(L0.ev_a, L0.stream));
     uint64_t done = 0;
     bool first_batch = true;
@@ -799,6 +800,7 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     } while (done < count);
     CUDA_TRY(cudaEventRecord(L0.ev_b, L0.stream));
     CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_acc, sizeof(double), cudaMemcpyDeviceToHost, L0.stream));
+    p->last_issue_ms = now_ms() - t_issue0;  // host time spent issuing the run (everything before the final wait)
     CUDA_TRY(cudaStreamSynchronize(L0.stream));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, L0.ev_a, L0.ev_b));
@@ -854,6 +856,7 @@ int tob_plan_set_stream(tob_plan* p, void* stream) {
 }
 
 double tob_plan_last_ms(const tob_plan* p) { return p->last_ms; }
+double tob_plan_last_issue_ms(const tob_plan* p) { return p->last_issue_ms; }
 int64_t tob_plan_last_launches(const tob_plan* p) { return p->last_launches; }
 
 int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_ops, double* result) {

@@ -270,6 +270,19 @@ __global__ void __launch_bounds__(256) k_reduce_splits(const double* __restrict_
     }
 }
 
+// few outputs, many splits (the final dot products): one warp per output, lane-strided partial sums, then
+// a fixed shuffle tree — deterministic, and 32 independent add chains instead of one
+__global__ void __launch_bounds__(256) k_reduce_splits_warp(const double* __restrict__ ws, double* __restrict__ c,
+                                                           unsigned long long outs, int nsplit, double modp, double inv_modp) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long o = blockIdx.x * 8ull + (threadIdx.x >> 5);
+    if (o >= outs) return;
+    double s = 0.0;
+    for (int j = lane; j < nsplit; j += 32) s += ws[(unsigned long long)j * outs + o];  // <= 32 residues per lane
+    s = warp_sum(s);                                                                    // <= 1024 residues: exact
+    if (lane == 0) c[o] = (modp > 0.0) ? mod_reduce(s, modp, inv_modp) : s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // DMMA GEMM
 // ------------------------------------------------------------------------------------------------
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     const unsigned long long Ksplit = (1ull << k) >> ks;
     const int KT = (int)((Ksplit + TK - 1) / TK);
     const bool partial = Ksplit < (unsigned long long)TK;  // K = 2, 4, 8 (< one K step): zero-fill the tail chunks
+    const int k4_end = partial ? (int)((Ksplit + 3) / 4) : K4;
     const double* A = operand_base(p.a, p.leaf_off, p.a_leaf) + ((tile_m << TM_LOG2) << k) + split * Ksplit;
     const double* B = operand_base(p.b, p.leaf_off, p.b_leaf) + ((tile_n << TN_LOG2) << k) + split * Ksplit;
 
@@ -390,6 +404,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
         for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS];
 #pragma unroll
         for (int k4 = 0; k4 < K4; k4++) {
+            if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
             const int cur = k4 & 1, nxt = cur ^ 1;
             if (k4 + 1 < K4) {
 #pragma unroll
@@ -941,7 +956,10 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (op.ksplit_log2 > 0) {
-        k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
+        if (outs <= 4096 && op.ksplit_log2 >= 5)
+            k_reduce_splits_warp<<<grid_for(outs, 8, cap), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
+        else
+            k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
         (*launches)++;
         e = cudaGetLastError();
     }

@@ -27,7 +27,7 @@ for n in range(lo, hi + 1, 10):
     for _ in range(5):
         cp.run()
         if best is None or cp.last_ms < best[0]:
-            best = (cp.last_ms, cp.last_gemm[0], cp.last_launches, cp.last_gemm[2])
+            best = (cp.last_ms, cp.last_gemm[0], cp.last_launches, cp.last_gemm[2], cp.last_issue_ms)
     one = None
     if cp.num_slices > 1:
         cp.run(first=0, count=1)
@@ -38,9 +38,9 @@ for n in range(lo, hi + 1, 10):
                  "gemm_launches": best[3], "one_slice_ms": one, "ops": len(d["slice_ops"]), "invariant_ops": len(d["invariant_ops"])})
     tot += best[0]
     totg += best[1]
-    print("n=%3d  %8.3f ms  gemm %8.3f  other %7.3f  launches %5d (gemm %3d)  ops/slice %3d  hoisted ops %3d  one slice %s" % (
+    print("n=%3d  %8.3f ms  gemm %8.3f  other %7.3f  launches %5d (gemm %3d)  ops/slice %3d  hoisted ops %3d  one slice %s  host issue %.3f ms" % (
         n, best[0], best[1], best[0] - best[1], best[2], best[3], len(d["slice_ops"]), len(d["invariant_ops"]),
-        "%.3f" % one if one else "-"), flush=True)
+        "%.3f" % one if one else "-", best[4]), flush=True)
     cp.close()
 print("total %.3f ms  gemm %.3f  other %.3f" % (tot, totg, tot - totg))
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)

@@ -4,7 +4,7 @@ T = fL + fR + k distinct indices (20..34), k contracted (2..16), fL = ceil((T-k)
 "ready" (contracted axes trailing in both operands = already canonical, no permutation) and "random"
 (seeded random axis order of each operand -> the stand-alone permute kernel runs first).  Reports the
 permute kernel (16 B moved per element), the contraction kernel (DMMA GEMM or generic) and their
-roofline fractions.  Usage: python tools/rank_sweep.py [--quick]"""
+roofline fractions.  Usage: python tools/rank_sweep.py [--quick] [--T=28,30] [--K=2,4]"""
 import ctypes, json, os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -17,6 +17,11 @@ FP64 = 35.49
 quick = "--quick" in sys.argv
 Ts = [20, 24, 28] if quick else list(range(20, 35, 2))
 Ks = [2, 8, 16] if quick else [2, 4, 8, 12, 16]
+for arg in sys.argv[1:]:  # --T=28,30  --K=2,4 : sub-grid
+    if arg.startswith("--T="):
+        Ts = [int(x) for x in arg[4:].split(",")]
+    if arg.startswith("--K="):
+        Ks = [int(x) for x in arg[4:].split(",")]
 P32 = ctypes.POINTER(ctypes.c_int32)
 rows = []
 for T in Ts:
