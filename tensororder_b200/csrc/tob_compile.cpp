@@ -439,35 +439,44 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         return op;
     };
 
-    // micro-closed subtrees
-    std::vector<char> closed(N, 0), is_root(N, 0), eff_dep(N, 0);
-    std::vector<int32_t> subtree_nodes(N, 1);
+    // ---- micro stages ----
+    // A join is "mini" when one CTA finishes it in about a launch latency (operands and result <= 2^14
+    // doubles, <= 2^17 multiply-adds).  Line-graph trees are chains of such joins hanging between a few large
+    // ones, so each phase (slice-invariant prologue / per-slice part) is cut into stages: stage L = ONE
+    // launch running every mini join of level L (one CTA per connected fragment of the tree, its joins in
+    // post-order with a CTA barrier in between), followed by the large joins of level L as kernels of their
+    // own.  level(mini) = max(level of mini children, 1 + level of large children); level(large) = max over
+    // its children: a join never runs before the stage that produces its operands.
+    const int kMiniRank = 14, kMiniWork = 17;
+    std::vector<char> mini(N, 0), phase(N, 1);
+    std::vector<int32_t> lvl(N, 0), subtree_nodes(N, 1), frag_root(N, -1);
     for (int i = 0; i < N; i++) {
         const NodeInfo& X = P->nodes[i];
-        eff_dep[i] = X.slice_dependent ? 1 : 0;
-        if (X.leaf >= 0) { closed[i] = 1; continue; }
+        phase[i] = (!hoist || X.slice_dependent) ? 1 : 0;
+        if (X.leaf >= 0) continue;
         subtree_nodes[i] = 1 + subtree_nodes[X.left] + subtree_nodes[X.right];
         const int k = P->nodes[X.left].k_with_sibling;
         const int m = (int)P->nodes[X.left].edges.size() - k, n = (int)P->nodes[X.right].edges.size() - k;
-        const bool tiny = (m + k <= 12 && n + k <= 12 && m + n <= 12 && m + n + k <= 15);
-        closed[i] = (opt.use_microtree && tiny && closed[X.left] && closed[X.right]) ? 1 : 0;
+        mini[i] = (opt.use_microtree && m + k <= kMiniRank && n + k <= kMiniRank && m + n <= kMiniRank &&
+                   m + n + k <= kMiniWork) ? 1 : 0;
+        int l = 0;
+        for (int c : {X.left, X.right}) {
+            if (P->nodes[c].leaf >= 0 || phase[c] != phase[i]) continue;  // leaves and hoisted results are just there
+            l = std::max(l, lvl[c] + ((mini[i] && !mini[c]) ? 1 : 0));
+        }
+        lvl[i] = l;
     }
-    for (int i = 0; i < N; i++) {
-        const NodeInfo& X = P->nodes[i];
-        if (X.leaf >= 0 || !closed[i]) continue;
-        is_root[i] = (X.parent < 0 || !closed[X.parent]) ? 1 : 0;
-    }
-    // every join of a micro subtree runs in the phase of the subtree's root
     for (int i = N - 1; i >= 0; i--) {
         const NodeInfo& X = P->nodes[i];
-        if (X.leaf >= 0 || !closed[i]) continue;
-        if (!is_root[i]) eff_dep[i] = eff_dep[X.parent];
+        if (X.leaf >= 0 || !mini[i]) continue;
+        const int pr = X.parent;
+        frag_root[i] = (pr >= 0 && mini[pr] && phase[pr] == phase[i] && lvl[pr] == lvl[i]) ? frag_root[pr] : i;
     }
     std::vector<char> persistent(N, 0);
     if (hoist) {
         for (int i = 0; i < N; i++) {
             const NodeInfo& X = P->nodes[i];
-            if (X.leaf < 0 && !eff_dep[i] && X.parent >= 0 && eff_dep[X.parent]) persistent[i] = 1;
+            if (X.leaf < 0 && !phase[i] && X.parent >= 0 && phase[X.parent]) persistent[i] = 1;
         }
     }
 
@@ -485,7 +494,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     auto emit = [&](int i, std::vector<Op>* list) {
         NodeInfo& X = P->nodes[i];
         Op op = build_op(i);
-        op.invariant = eff_dep[i] ? 0 : 1;
+        op.invariant = phase[i] ? 0 : 1;
         choose_kernel(&op, opt.kernel_policy, true);
         place(op, i);
         if (op.ksplit_log2 > 0) {
@@ -498,39 +507,41 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         }
         list->push_back(op);
     };
-    auto run_phase = [&](int dep, std::vector<Op>* list, int which) {
-        // 1. all micro subtrees of this phase: one launch, one CTA per (packed) subtree
-        MicroProgram& mp = P->micro[which];
-        arena.barrier();  // a new phase starts after everything before it has finished
-        std::vector<std::vector<Op>> subtrees;
+    auto run_stage = [&](int dep, int level, std::vector<Op>* list) {
+        arena.barrier();  // everything released so far is ordered before this stage
+        // 1. the mini joins of this level: one launch, one CTA per (packed) fragment
+        std::vector<std::vector<Op>> frags;
         std::vector<double> work;
+        std::vector<int32_t> frag_of_root(N, -1);
         std::vector<std::pair<int64_t, int64_t>> deferred;  // arena space freed only after the launch
-        for (int r = 0; r < N; r++) {
-            if (!is_root[r] || eff_dep[r] != dep) continue;
-            subtrees.emplace_back();
-            work.push_back(0.0);
-            for (int i = r - subtree_nodes[r] + 1; i <= r; i++) {
-                NodeInfo& X = P->nodes[i];
-                if (X.leaf >= 0) continue;
-                Op op = build_op(i);
-                op.invariant = dep ? 0 : 1;
-                op.kind = OP_GENERIC;
-                op.threads_per_out = 1;
-                op.flops = 2.0 * std::ldexp(1.0, op.m + op.n + op.k);
-                op.bytes = 8.0 * (std::ldexp(1.0, op.m + op.k) + std::ldexp(1.0, op.n + op.k) + std::ldexp(1.0, op.m + op.n));
-                place(op, i);
-                for (int c : {X.left, X.right}) {
-                    const NodeInfo& Cn = P->nodes[c];
-                    if (Cn.leaf < 0 && !persistent[c]) deferred.emplace_back(Cn.where.offset, size_of[c]);
-                }
-                // cost model for packing: per-join latency floor + multiply-adds
-                work.back() += 2000.0 + std::ldexp(1.0, op.m + op.n + op.k);
-                subtrees.back().push_back(op);
+        int max_outs_log2 = 0;
+        for (int i = 0; i < N; i++) {
+            NodeInfo& X = P->nodes[i];
+            if (X.leaf >= 0 || !mini[i] || phase[i] != dep || lvl[i] != level) continue;
+            int32_t& f = frag_of_root[frag_root[i]];
+            if (f < 0) { f = (int32_t)frags.size(); frags.emplace_back(); work.push_back(0.0); }
+            Op op = build_op(i);
+            op.invariant = dep ? 0 : 1;
+            op.kind = OP_GENERIC;
+            op.threads_per_out = 1;
+            op.flops = 2.0 * std::ldexp(1.0, op.m + op.n + op.k);
+            op.bytes = 8.0 * (std::ldexp(1.0, op.m + op.k) + std::ldexp(1.0, op.n + op.k) + std::ldexp(1.0, op.m + op.n));
+            place(op, i);
+            for (int c : {X.left, X.right}) {
+                const NodeInfo& Cn = P->nodes[c];
+                if (Cn.leaf < 0 && !persistent[c]) deferred.emplace_back(Cn.where.offset, size_of[c]);
             }
+            max_outs_log2 = std::max(max_outs_log2, op.m + op.n);
+            // cost model for packing: per-join latency floor + multiply-adds
+            work[f] += 2000.0 + std::ldexp(1.0, op.m + op.n + op.k);
+            frags[f].push_back(op);
         }
-        if (!subtrees.empty()) {
-            const int n_cta = (int)std::min<size_t>(subtrees.size(), 2 * kNumSMs);
-            std::vector<size_t> order(subtrees.size());
+        if (!frags.empty()) {
+            P->micro.emplace_back();
+            MicroProgram& mp = P->micro.back();
+            mp.threads = max_outs_log2 > 12 ? 1024 : 256;
+            const int n_cta = (int)std::min<size_t>(frags.size(), 2 * kNumSMs);
+            std::vector<size_t> order(frags.size());
             for (size_t j = 0; j < order.size(); j++) order[j] = j;
             std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return work[a] > work[b]; });
             std::vector<std::vector<size_t>> bins(n_cta);
@@ -544,29 +555,29 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             }
             mp.cta_start.push_back(0);
             for (int c = 0; c < n_cta; c++) {
+                std::sort(bins[c].begin(), bins[c].end());  // fragments of one stage are independent; keep tree order
                 for (size_t j : bins[c])
-                    for (const Op& op : subtrees[j]) mp.ops.push_back(op);
+                    for (const Op& op : frags[j]) mp.ops.push_back(op);
                 mp.cta_start.push_back((int32_t)mp.ops.size());
             }
             Op launch;
             launch.kind = OP_MICRO;
-            launch.micro_which = which;
+            launch.micro_which = (int32_t)P->micro.size() - 1;
             launch.invariant = dep ? 0 : 1;
             for (const Op& op : mp.ops) { launch.flops += op.flops; launch.bytes += op.bytes; }
             list->push_back(launch);
             for (auto& d : deferred) arena.release(d.first, d.second);
+            arena.barrier();  // the launch orders everything released so far
         }
-        arena.barrier();  // the micro launch (or the phase start) orders everything released so far
-        // 2. the other joins of this phase, post-order
+        // 2. the large joins of this level, post-order
         for (int i = 0; i < N; i++)
-            if (P->nodes[i].leaf < 0 && !closed[i] && eff_dep[i] == dep) emit(i, list);
+            if (P->nodes[i].leaf < 0 && !mini[i] && phase[i] == dep && lvl[i] == level) emit(i, list);
     };
-    if (hoist) {
-        run_phase(0, &P->invariant_ops, 0);
-        run_phase(1, &P->slice_ops, 1);
-    } else {
-        for (int i = 0; i < N; i++) eff_dep[i] = 1;
-        run_phase(1, &P->slice_ops, 1);
+    for (int dep = hoist ? 0 : 1; dep <= 1; dep++) {
+        int max_level = -1;
+        for (int i = 0; i < N; i++)
+            if (P->nodes[i].leaf < 0 && phase[i] == dep) max_level = std::max(max_level, lvl[i]);
+        for (int level = 0; level <= max_level; level++) run_stage(dep, level, dep ? &P->slice_ops : &P->invariant_ops);
     }
     P->root = P->nodes[N - 1].where;
     Op acc;
@@ -599,7 +610,7 @@ std::string describe(const Program& P) {
             if (i) o << ",";
             if (op.kind == OP_MICRO) {
                 const MicroProgram& mp = P.micro[op.micro_which];
-                o << "{\"kind\":3,\"which\":" << op.micro_which << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops
+                o << "{\"kind\":3,\"which\":" << op.micro_which << ",\"threads\":" << mp.threads << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops
                   << ",\"bytes\":" << op.bytes << ",\"cta_start\":[";
                 for (size_t j = 0; j < mp.cta_start.size(); j++) o << (j ? "," : "") << mp.cta_start[j];
                 o << "],\"micro\":";

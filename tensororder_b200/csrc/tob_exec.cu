@@ -68,8 +68,8 @@ struct tob_plan {
     double* d_results = nullptr;
     int32_t* d_term_start = nullptr;
     uint8_t *d_id_bit = nullptr, *d_addr_bit = nullptr;
-    MicroOpDev* d_micro_ops[2] = {nullptr, nullptr};
-    int32_t* d_micro_start[2] = {nullptr, nullptr};
+    std::vector<MicroOpDev*> d_micro_ops;   // per micro stage
+    std::vector<int32_t*> d_micro_start;
     // one pinned block mirroring the prefix of the device block up to the end of the leaves
     void* h_block = nullptr;
     size_t h_block_size = 0;
@@ -297,7 +297,7 @@ int tob_plan_create(const tob_plan_desc* desc, const tob_options* opt, tob_plan*
 
 int64_t tob_plan_peak_bytes(const tob_plan* p) {
     size_t tables = 4096 + 32 * p->prog.leaves.size();
-    for (int w = 0; w < 2; w++) tables += p->prog.micro[w].ops.size() * sizeof(MicroOpDev) + p->prog.micro[w].cta_start.size() * 4 + 1024;
+    for (const MicroProgram& mp : p->prog.micro) tables += mp.ops.size() * sizeof(MicroOpDev) + mp.cta_start.size() * 4 + 1024;
     for (const LeafInfo& L : p->prog.leaves) tables += 2 * L.slice_id_bit.size();
     tables += kMaxResults * 8;
     const int64_t lanes = p->prog.lanes;
@@ -347,7 +347,8 @@ static void release_device(tob_plan* p) {
     p->d_block = nullptr; p->h_block = nullptr;
     p->d_term_start = nullptr; p->d_id_bit = nullptr; p->d_addr_bit = nullptr;
     p->h_state = nullptr; p->h_readback = nullptr;
-    for (int w = 0; w < 2; w++) { p->d_micro_ops[w] = nullptr; p->d_micro_start[w] = nullptr; }
+    p->d_micro_ops.clear();
+    p->d_micro_start.clear();
     p->uploaded = false;
     p->runs = 0;
 }
@@ -442,8 +443,9 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     const size_t o_term = section(sizeof(int32_t) * (L + 1));
     const size_t o_idb = section(id_bit.size() + 1);
     const size_t o_adb = section(addr_bit.size() + 1);
-    size_t o_mops[2], o_mstart[2];
-    for (int w = 0; w < 2; w++) {
+    const int NM = (int)G.micro.size();
+    std::vector<size_t> o_mops(NM), o_mstart(NM);
+    for (int w = 0; w < NM; w++) {
         o_mops[w] = section(G.micro[w].ops.size() * sizeof(MicroOpDev) + 8);
         o_mstart[w] = section(G.micro[w].cta_start.size() * sizeof(int32_t) + 8);
     }
@@ -486,7 +488,9 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     p->d_term_start = reinterpret_cast<int32_t*>(d + o_term);
     p->d_id_bit = reinterpret_cast<uint8_t*>(d + o_idb);
     p->d_addr_bit = reinterpret_cast<uint8_t*>(d + o_adb);
-    for (int w = 0; w < 2; w++) {
+    p->d_micro_ops.resize(NM);
+    p->d_micro_start.resize(NM);
+    for (int w = 0; w < NM; w++) {
         p->d_micro_ops[w] = reinterpret_cast<MicroOpDev*>(d + o_mops[w]);
         p->d_micro_start[w] = reinterpret_cast<int32_t*>(d + o_mstart[w]);
     }
@@ -502,7 +506,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         memcpy(h + o_idb, id_bit.data(), id_bit.size());
         memcpy(h + o_adb, addr_bit.data(), addr_bit.size());
     }
-    for (int w = 0; w < 2; w++) {
+    for (int w = 0; w < NM; w++) {
         const MicroProgram& mp = G.micro[w];
         MicroOpDev* mo = reinterpret_cast<MicroOpDev*>(h + o_mops[w]);
         for (size_t j = 0; j < mp.ops.size(); j++) {
@@ -605,7 +609,7 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
         int max_ops = 1;
         for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
         const int smem_ops = std::min(max_ops, (int)(64 * 1024 / sizeof(MicroOpDev)));
-        return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops,
+        return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops, mp.threads,
                                 p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, p->modulus, stream);
     }
     KParams k = make_params(p, L, op);

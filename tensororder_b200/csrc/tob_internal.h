@@ -19,7 +19,7 @@ enum OpKind : int32_t {
     OP_GENERIC = 0,  // thread / warp / CTA per output element, bandwidth-bound
     OP_GEMM = 1,     // DMMA tile kernel, compute-bound
     OP_ACCUM = 2,    // acc += root scalar
-    OP_MICRO = 3,    // one launch executing every join of the tiny ("micro-closed") subtrees, one CTA per subtree
+    OP_MICRO = 3,    // one launch executing every mini join of one stage, one CTA per tree fragment
 };
 
 struct OperandRef {
@@ -53,12 +53,12 @@ struct Op {
     std::vector<int32_t> waits;
 };
 
-// Tiny subtrees (every operand and result <= 2^12 doubles, <= 2^15 multiply-adds per join, closed under
-// descendants) depend only on leaves: all of them run in one launch, each subtree sequentially inside
-// one CTA with __syncthreads between its joins.
+// One micro stage (tob_compile.cpp "micro stages"): every mini join of one level of one phase, grouped by
+// CTA; inside a CTA the joins run one after the other with a CTA barrier in between.
 struct MicroProgram {
-    std::vector<Op> ops;              // grouped by CTA, post-order inside a subtree
+    std::vector<Op> ops;              // grouped by CTA, post-order inside a fragment
     std::vector<int32_t> cta_start;   // [n_ctas + 1]
+    int32_t threads = 256;            // CTA size: 1024 when the stage has results above 2^12 doubles
 };
 
 struct LeafInfo {
@@ -89,7 +89,7 @@ struct Program {
     std::vector<LeafInfo> leaves;
     std::vector<Op> invariant_ops;    // run once per tob_plan_run
     std::vector<Op> slice_ops;        // run once per slice
-    MicroProgram micro[2];            // [0] invariant phase, [1] slice phase
+    std::vector<MicroProgram> micro;  // micro stages, in execution order (Op::micro_which indexes this)
     int64_t leaf_doubles = 0;         // device leaf region
     int64_t arena_doubles = 0;        // intermediates
     int64_t ws_doubles = 0;           // split-K workspace

@@ -680,6 +680,7 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
 #define GEMM_76_WZ2_X k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2, true>
 
+template <int NT>
 __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
                             double* arena, const double* arena0, const long long* leaf_off, int smem_ops, double modp);
 
@@ -711,7 +712,10 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ2_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_microtree, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(k_microtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_microtree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
     return e;
 }
@@ -801,9 +805,10 @@ __device__ __forceinline__ double micro_dot(const double* ar, const double* br, 
 // walks is latency-bound: with the descriptors and the (tiny) leaf operands staged up front and each
 // result handed to the next join through the forward buffer, the critical path of a join is shared-memory
 // latency instead of two L2 round trips (store result, load it back).
-__global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
-                                                   const double* leaves, double* arena, const double* arena0,
-                                                   const long long* leaf_off, int smem_ops, double modp) {
+template <int NT>
+__global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
+                                                  const double* leaves, double* arena, const double* arena0,
+                                                  const long long* leaf_off, int smem_ops, double modp) {
     extern __shared__ __align__(16) unsigned char micro_smem[];
     MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
     double* cache = reinterpret_cast<double*>(micro_smem + (size_t)smem_ops * sizeof(MicroOpDev));
@@ -814,10 +819,10 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
         const int4* src = reinterpret_cast<const int4*>(ops + first);
         int4* dst = reinterpret_cast<int4*>(sops);
         const int n16 = (last - first) * (int)(sizeof(MicroOpDev) / 16);
-        for (int i = threadIdx.x; i < n16; i += 256) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n16; i += NT) dst[i] = src[i];
         __syncthreads();
         // leaf operands: one thread per (join, operand), a handful of doubles each
-        for (int i = threadIdx.x; i < 2 * (last - first); i += 256) {
+        for (int i = threadIdx.x; i < 2 * (last - first); i += NT) {
             const MicroOpDev& op = sops[i >> 1];
             const bool is_b = i & 1;
             if ((is_b ? op.b_src : op.a_src) != 2) continue;
@@ -845,7 +850,7 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
         const unsigned outs = 1u << tot;
         const unsigned mask = op.mask_m;
         const bool fwd_out = staged && op.fwd_out;
-        for (unsigned c = threadIdx.x; c < outs; c += 256) {
+        for (unsigned c = threadIdx.x; c < outs; c += NT) {
             unsigned mi = 0, ni = 0, im = 0, in = 0;
             for (int b = 0; b < tot; b++) {
                 const unsigned bit = (c >> b) & 1u;
@@ -860,11 +865,14 @@ __global__ void __launch_bounds__(256) k_microtree(const MicroOpDev* __restrict_
     }
 }
 
-cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, int threads, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, double modp,
                              cudaStream_t stream) {
     const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double);
-    k_microtree<<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
+    if (threads > 256)  // stages with results above 2^12 doubles: four times the threads per fragment
+        k_microtree<1024><<<n_ctas, 1024, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
+    else
+        k_microtree<256><<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
     return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ struct KParams {
     double modp, inv_modp;
 };
 
-// One join of a micro subtree (device copy).  m + n <= 12, operands <= 2^12 doubles.
+// One join of a micro stage (device copy).  m + n <= 14 (mask_m has 16 bits), operands <= 2^14 doubles.
 struct MicroOpDev {
     long long a_off, b_off, c_off;  // doubles: a/b inside their space, c inside the arena
     int32_t a_leaf, b_leaf;         // leaf_off index or -1
@@ -80,7 +80,7 @@ struct PermuteParams {
 };
 
 cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream, int* launches);
-cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, const double* leaves,
+cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, int threads, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, double modp,
                              cudaStream_t stream);
 cudaError_t launch_accum(DevState* st, const double* root, const long long* leaf_off, int root_leaf, double* results,

@@ -102,7 +102,8 @@ def test_forced_generic_policy_and_gemm_selection():
 
 @pytest.mark.parametrize("name,variant", [("vc50_lineflow", None), ("vc100_lineflow", "min4"), ("vc150_lineflow", None)])
 def test_micro_subtrees(name, variant):
-    """Tiny subtrees collapse into one launch per phase; results are unchanged with the feature off."""
+    """Mini joins collapse into one launch per stage (level of a phase); results are unchanged with the
+    feature off."""
     pp = load_golden(name)
     if variant:
         pp = pp.variant(variant)
@@ -111,8 +112,9 @@ def test_micro_subtrees(name, variant):
     off = CompiledPlan(flat, use_microtree=False).describe()
     n_joins = sum(1 for n in pp.postorder if len(n) == 2)
     assert sum(1 for op in off["slice_ops"] + off["invariant_ops"] if op["kind"] in (0, 1)) == n_joins
-    micro = [op for op in on["slice_ops"] + on["invariant_ops"] if op["kind"] == 3]
-    assert 1 <= len(micro) <= 2
+    micro = [op for op in on["invariant_ops"] + on["slice_ops"] if op["kind"] == 3]
+    assert 1 <= len(micro) <= 8
+    assert [op["which"] for op in micro] == list(range(len(micro)))  # stages in execution order
     in_micro = sum(len(op["micro"]) for op in micro)
     rest = sum(1 for op in on["slice_ops"] + on["invariant_ops"] if op["kind"] in (0, 1))
     assert in_micro + rest == n_joins and in_micro > n_joins // 3
@@ -155,7 +157,7 @@ def test_dag_schedule_orders_every_hazard(name, variant):
     assert one["branches"] == 1 and all(not op.get("waits") for op in one["invariant_ops"] + one["slice_ops"])
     # the point of the schedule: the longest chain is far shorter than the op count
     if name == "vc150_lineflow" and variant is None:
-        desc = CompiledPlan(flat).describe()
+        desc = CompiledPlan(flat, use_microtree=False).describe()
         ops = desc["slice_ops"]
         depth = [0] * len(ops)
         last = {}
