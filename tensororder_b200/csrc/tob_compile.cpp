@@ -441,15 +441,20 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
 
     // ---- micro stages ----
     // A join is "mini" when one CTA finishes it in about a launch latency (operands and result <= 2^14
-    // doubles, <= 2^17 multiply-adds).  Line-graph trees are chains of such joins hanging between a few large
-    // ones, so each phase (slice-invariant prologue / per-slice part) is cut into stages: stage L = ONE
-    // launch running every mini join of level L (one CTA per connected fragment of the tree, its joins in
-    // post-order with a CTA barrier in between), followed by the large joins of level L as kernels of their
-    // own.  level(mini) = max(level of mini children, 1 + level of large children); level(large) = max over
-    // its children: a join never runs before the stage that produces its operands.
-    const int kMiniRank = 14, kMiniWork = 17;
+    // doubles, <= 2^17 multiply-adds).  Line-graph trees are long chains of such joins — a running
+    // intermediate absorbing one small tensor after the other — hanging between a few large joins.  Each
+    // phase (slice-invariant prologue / per-slice part) is cut into stages: stage L = ONE launch running
+    // every mini join of level L, one CTA per CHAIN (each join consumes the previous one's result, handed
+    // over in shared memory), followed by the large joins of level L as kernels of their own.  Levels are
+    // Strahler numbers: a mini join continues the chain of its highest-level mini child; two mini children
+    // of equal level end both chains and start a new one a level up; a large child pushes its consumer one
+    // level up; a large join runs after the stage of its highest child.  Chains of one stage are therefore
+    // independent, everything a stage reads was produced by an earlier stage (or earlier in its own chain),
+    // and the number of stages grows with the tree's branching depth (2-5), not with its size.
+    static const int kMiniRank = getenv("TOB_MINI_RANK") ? std::min(14, std::max(4, atoi(getenv("TOB_MINI_RANK")))) : 14;  // experiments
+    const int kMiniWork = kMiniRank + 3;
     std::vector<char> mini(N, 0), phase(N, 1);
-    std::vector<int32_t> lvl(N, 0), subtree_nodes(N, 1), frag_root(N, -1);
+    std::vector<int32_t> lvl(N, 0), subtree_nodes(N, 1), frag_root(N, -1);  // frag_root: first join of the chain
     for (int i = 0; i < N; i++) {
         const NodeInfo& X = P->nodes[i];
         phase[i] = (!hoist || X.slice_dependent) ? 1 : 0;
@@ -457,20 +462,20 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         subtree_nodes[i] = 1 + subtree_nodes[X.left] + subtree_nodes[X.right];
         const int k = P->nodes[X.left].k_with_sibling;
         const int m = (int)P->nodes[X.left].edges.size() - k, n = (int)P->nodes[X.right].edges.size() - k;
+        // k <= 4: a thread walks the contracted range of its output alone, 16 terms at most (the dot products
+        // near the root have few outputs and a long K: those go to the warp / CTA-per-output kernels)
         mini[i] = (opt.use_microtree && m + k <= kMiniRank && n + k <= kMiniRank && m + n <= kMiniRank &&
-                   m + n + k <= kMiniWork) ? 1 : 0;
-        int l = 0;
+                   m + n + k <= kMiniWork && k <= 4) ? 1 : 0;
+        int l = 0, n_at = 0, cont = -1;  // highest child level, mini children at that level, one of them
         for (int c : {X.left, X.right}) {
             if (P->nodes[c].leaf >= 0 || phase[c] != phase[i]) continue;  // leaves and hoisted results are just there
-            l = std::max(l, lvl[c] + ((mini[i] && !mini[c]) ? 1 : 0));
+            const int e = lvl[c] + ((mini[i] && !mini[c]) ? 1 : 0);
+            if (e > l) { l = e; n_at = 0; cont = -1; }
+            if (e == l && mini[c]) { n_at++; cont = c; }
         }
-        lvl[i] = l;
-    }
-    for (int i = N - 1; i >= 0; i--) {
-        const NodeInfo& X = P->nodes[i];
-        if (X.leaf >= 0 || !mini[i]) continue;
-        const int pr = X.parent;
-        frag_root[i] = (pr >= 0 && mini[pr] && phase[pr] == phase[i] && lvl[pr] == lvl[i]) ? frag_root[pr] : i;
+        if (!mini[i]) { lvl[i] = l; continue; }
+        if (n_at == 2) { lvl[i] = l + 1; frag_root[i] = i; }
+        else { lvl[i] = l; frag_root[i] = (n_at == 1 && lvl[cont] == l) ? frag_root[cont] : i; }
     }
     std::vector<char> persistent(N, 0);
     if (hoist) {
@@ -509,7 +514,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     };
     auto run_stage = [&](int dep, int level, std::vector<Op>* list) {
         arena.barrier();  // everything released so far is ordered before this stage
-        // 1. the mini joins of this level: one launch, one CTA per (packed) fragment
+        // 1. the mini joins of this level: one launch, one CTA per (packed) chain
         std::vector<std::vector<Op>> frags;
         std::vector<double> work;
         std::vector<int32_t> frag_of_root(N, -1);
@@ -539,7 +544,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         if (!frags.empty()) {
             P->micro.emplace_back();
             MicroProgram& mp = P->micro.back();
-            mp.threads = max_outs_log2 > 12 ? 1024 : 256;
+            mp.threads = max_outs_log2 > 10 ? 1024 : 256;
             const int n_cta = (int)std::min<size_t>(frags.size(), 2 * kNumSMs);
             std::vector<size_t> order(frags.size());
             for (size_t j = 0; j < order.size(); j++) order[j] = j;

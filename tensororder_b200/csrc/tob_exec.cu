@@ -528,7 +528,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
                 const Op& op = mp.ops[j];
                 if (j > mp.cta_start[c]) {
                     const Op& prev = mp.ops[j - 1];
-                    const bool small = ((int64_t)1 << (prev.m + prev.n)) <= kMicroFwdMax;
+                    const bool small = ((int64_t)1 << (prev.m + prev.n)) <= (mp.threads > 256 ? kMicroFwdMaxBig : kMicroFwdMax);
                     if (small && op.a.space != 0 && op.a.node == prev.node) { mo[j].a_src = 1; mo[j - 1].fwd_out = 1; }
                     if (small && op.b.space != 0 && op.b.node == prev.node) { mo[j].b_src = 1; mo[j - 1].fwd_out = 1; }
                 }
@@ -608,7 +608,7 @@ static cudaError_t launch_op(tob_plan* p, const Lane& L, const Op& op, int* laun
         const MicroProgram& mp = p->prog.micro[w];
         int max_ops = 1;
         for (size_t c = 0; c + 1 < mp.cta_start.size(); c++) max_ops = std::max(max_ops, mp.cta_start[c + 1] - mp.cta_start[c]);
-        const int smem_ops = std::min(max_ops, (int)(64 * 1024 / sizeof(MicroOpDev)));
+        const int smem_ops = std::min(max_ops, (int)(kMicroDescBytes / sizeof(MicroOpDev)));
         return launch_microtree(p->d_micro_ops[w], p->d_micro_start[w], (int)mp.cta_start.size() - 1, smem_ops, mp.threads,
                                 p->d_leaves, L.d_arena, p->lane[0].d_arena, L.d_leaf_off, p->modulus, stream);
     }

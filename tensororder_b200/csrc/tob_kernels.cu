@@ -680,7 +680,7 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
 #define GEMM_76_WZ2_X k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2, true>
 
-template <int NT>
+template <int NT, int FWD>
 __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
                             double* arena, const double* arena0, const long long* leaf_off, int smem_ops, double modp);
 
@@ -712,11 +712,11 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ2_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_microtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
+    e = cudaFuncSetAttribute(k_microtree<256, kMicroFwdMax>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kMicroDescBytes + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_microtree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             64 * 1024 + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
+    e = cudaFuncSetAttribute(k_microtree<1024, kMicroFwdMaxBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kMicroDescBytes + (int)((kMicroLeafCache + 2 * kMicroFwdMaxBig) * sizeof(double)));
     return e;
 }
 
@@ -777,44 +777,27 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 // so a __syncthreads between joins is the only synchronisation.  Replaces hundreds of launch-bound
 // kernel launches per slice by one.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double micro_dot(const double* ar, const double* br, int k, bool a_glob, bool b_glob, double modp) {
-    if (k == 0) {
-        const double s = (a_glob ? __ldcg(ar) : ar[0]) * (b_glob ? __ldcg(br) : br[0]);
-        return modp > 0.0 ? mod_reduce(s, modp, 1.0 / modp) : s;
-    }
-    const double2* a2 = reinterpret_cast<const double2*>(ar);
-    const double2* b2 = reinterpret_cast<const double2*>(br);
-    const int K2 = 1 << (k - 1);
-    const double inv = modp > 0.0 ? 1.0 / modp : 0.0;
-    double s0 = 0.0, s1 = 0.0;
-    for (int j = 0; j < K2; j++) {
-        const double2 x = a_glob ? __ldcg(a2 + j) : a2[j];
-        const double2 y = b_glob ? __ldcg(b2 + j) : b2[j];
-        s0 = fma(x.x, y.x, s0);
-        s1 = fma(x.y, y.y, s1);
-        if (modp > 0.0 && (j & 63) == 63) {  // exact mode: reduce before 65 products pile up
-            s0 = mod_reduce(s0, modp, inv);
-            s1 = mod_reduce(s1, modp, inv);
-        }
-    }
-    const double s = s0 + s1;
-    return modp > 0.0 ? mod_reduce(s, modp, inv) : s;
-}
-
 // Shared memory: [join descriptors | leaf cache | two forward buffers].  The serial chain of joins a CTA
 // walks is latency-bound: with the descriptors and the (tiny) leaf operands staged up front and each
 // result handed to the next join through the forward buffer, the critical path of a join is shared-memory
-// latency instead of two L2 round trips (store result, load it back).
-template <int NT>
+// latency instead of two L2 round trips (store result, load it back).  Operands that do come from global
+// memory are fetched for U = 4 outputs at a time, so a thread has 8 independent L2 requests in flight
+// instead of one dependent round trip per output; the address bits of an output that come from the thread
+// index are decoded once per join, only the few bits above log2(NT) per output.
+template <int NT, int FWD>
 __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
                                                   const double* leaves, double* arena, const double* arena0,
                                                   const long long* leaf_off, int smem_ops, double modp) {
+    constexpr int U = 4;
+    constexpr int LOG_NT = NT == 1024 ? 10 : 8;
+    static_assert(NT == (1 << LOG_NT), "NT");
     extern __shared__ __align__(16) unsigned char micro_smem[];
     MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
     double* cache = reinterpret_cast<double*>(micro_smem + (size_t)smem_ops * sizeof(MicroOpDev));
-    double* fwd = cache + kMicroLeafCache;  // [2][kMicroFwdMax]
+    double* fwd = cache + kMicroLeafCache;  // [2][FWD]
     const int first = cta_start[blockIdx.x], last = cta_start[blockIdx.x + 1];
     const bool staged = (last - first) <= smem_ops;
+    const double inv = modp > 0.0 ? 1.0 / modp : 0.0;
     if (staged) {
         const int4* src = reinterpret_cast<const int4*>(ops + first);
         int4* dst = reinterpret_cast<int4*>(sops);
@@ -837,8 +820,8 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
     for (int i = first; i < last; i++) {
         const MicroOpDev op = staged ? sops[i - first] : ops[i];
         const int a_src = staged ? op.a_src : 0, b_src = staged ? op.b_src : 0;
-        const double* prev = fwd + ((i - first + 1) & 1) * kMicroFwdMax;  // written by join i-1
-        double* mine = fwd + ((i - first) & 1) * kMicroFwdMax;
+        const double* prev = fwd + ((i - first + 1) & 1) * FWD;  // written by join i-1
+        double* mine = fwd + ((i - first) & 1) * FWD;
         const double* A = a_src == 1 ? prev : a_src == 2 ? cache + op.a_soff
                           : (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
                                 (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
@@ -850,16 +833,79 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
         const unsigned outs = 1u << tot;
         const unsigned mask = op.mask_m;
         const bool fwd_out = staged && op.fwd_out;
-        for (unsigned c = threadIdx.x; c < outs; c += NT) {
-            unsigned mi = 0, ni = 0, im = 0, in = 0;
-            for (int b = 0; b < tot; b++) {
-                const unsigned bit = (c >> b) & 1u;
-                if ((mask >> b) & 1u) { mi |= bit << im; im++; }
-                else { ni |= bit << in; in++; }
+        const bool a_glob = a_src == 0, b_glob = b_src == 0;
+        // address bits supplied by the thread index: decoded once per join
+        unsigned mi_lo = 0, ni_lo = 0;
+        int im_lo = 0, in_lo = 0;
+        const int lo_bits = tot < LOG_NT ? tot : LOG_NT;
+        for (int b = 0; b < lo_bits; b++) {
+            const unsigned bit = (threadIdx.x >> b) & 1u;
+            if ((mask >> b) & 1u) { mi_lo |= bit << im_lo; im_lo++; }
+            else { ni_lo |= bit << in_lo; in_lo++; }
+        }
+        for (unsigned c0 = threadIdx.x; c0 < outs; c0 += NT * U) {
+            const double* ar[U];
+            const double* br[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned c = c0 + u * NT;
+                unsigned mi = mi_lo, ni = ni_lo;
+                int im = im_lo, in = in_lo;
+                for (int b = LOG_NT; b < tot; b++) {
+                    const unsigned bit = (c >> b) & 1u;
+                    if ((mask >> b) & 1u) { mi |= bit << im; im++; }
+                    else { ni |= bit << in; in++; }
+                }
+                const bool ok = c < outs;  // rows of a dead slot point at row 0: loaded, never stored
+                ar[u] = A + (ok ? ((size_t)mi << k) : 0);
+                br[u] = B + (ok ? ((size_t)ni << k) : 0);
             }
-            const double s = micro_dot(A + ((size_t)mi << k), B + ((size_t)ni << k), k, a_src == 0, b_src == 0, modp);
-            C[c] = s;
-            if (fwd_out) mine[c] = s;
+            double s[U];
+            if (k == 0) {
+                double x[U], y[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) x[u] = a_glob ? __ldcg(ar[u]) : ar[u][0];
+#pragma unroll
+                for (int u = 0; u < U; u++) y[u] = b_glob ? __ldcg(br[u]) : br[u][0];
+#pragma unroll
+                for (int u = 0; u < U; u++) s[u] = x[u] * y[u];
+            } else {
+                const int K2 = 1 << (k - 1);
+                double s0[U], s1[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) s0[u] = s1[u] = 0.0;
+                for (int j = 0; j < K2; j++) {
+                    double2 x[U], y[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        x[u] = a_glob ? __ldcg(reinterpret_cast<const double2*>(ar[u]) + j) : reinterpret_cast<const double2*>(ar[u])[j];
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        y[u] = b_glob ? __ldcg(reinterpret_cast<const double2*>(br[u]) + j) : reinterpret_cast<const double2*>(br[u])[j];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        s0[u] = fma(x[u].x, y[u].x, s0[u]);
+                        s1[u] = fma(x[u].y, y[u].y, s1[u]);
+                    }
+                    if (modp > 0.0 && (j & 63) == 63) {  // exact mode: reduce before 65 products pile up
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            s0[u] = mod_reduce(s0[u], modp, inv);
+                            s1[u] = mod_reduce(s1[u], modp, inv);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) s[u] = s0[u] + s1[u];
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned c = c0 + u * NT;
+                if (c >= outs) continue;
+                const double v = modp > 0.0 ? mod_reduce(s[u], modp, inv) : s[u];
+                C[c] = v;
+                if (fwd_out) mine[c] = v;
+            }
         }
         __syncthreads();
     }
@@ -868,11 +914,13 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
 cudaError_t launch_microtree(const MicroOpDev* ops, const int32_t* cta_start, int n_ctas, int smem_ops, int threads, const double* leaves,
                              double* arena, const double* arena0, const long long* leaf_off, double modp,
                              cudaStream_t stream) {
-    const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double);
-    if (threads > 256)  // stages with results above 2^12 doubles: four times the threads per fragment
-        k_microtree<1024><<<n_ctas, 1024, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
-    else
-        k_microtree<256><<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
+    if (threads > 256) {  // stages with results above 2^12 doubles: four times the threads and forward buffers
+        const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMaxBig) * sizeof(double);
+        k_microtree<1024, kMicroFwdMaxBig><<<n_ctas, 1024, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
+    } else {
+        const size_t smem = (size_t)smem_ops * sizeof(MicroOpDev) + (size_t)(kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double);
+        k_microtree<256, kMicroFwdMax><<<n_ctas, 256, smem, stream>>>(ops, cta_start, leaves, arena, arena0, leaf_off, smem_ops, modp);
+    }
     return cudaGetLastError();
 }
 

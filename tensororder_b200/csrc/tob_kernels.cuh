@@ -47,7 +47,9 @@ struct MicroOpDev {
     uint16_t pad2;                  // 48 bytes: descriptors are staged into shared memory with 16-byte copies
 };
 constexpr int kMicroLeafCache = 2048;   // doubles of staged leaves per CTA
-constexpr int kMicroFwdMax = 2048;      // largest result (doubles) forwarded through shared memory
+constexpr int kMicroFwdMax = 2048;      // largest result (doubles) forwarded through shared memory (256-thread stages)
+constexpr int kMicroFwdMaxBig = 8192;   // same for the 1024-thread stages (2 x 64 KB of forward buffers)
+constexpr int kMicroDescBytes = 48 * 1024;  // shared memory for staged join descriptors (1024 joins per CTA)
 constexpr int kMicroStageMax = 64;      // largest leaf operand (doubles) staged
 static_assert(sizeof(MicroOpDev) % 16 == 0, "MicroOpDev is staged with 16-byte copies");
 

@@ -111,8 +111,8 @@ def run_program(desc, flat, first=0, count=None, stride=1, modulus=0, dag_seed=N
             assert op["cta_start"][0] == 0 and op["cta_start"][-1] == len(op["micro"])
             for sub in op["micro"]:
                 assert sub["m"] + sub["n"] <= 14 and sub["m"] + sub["k"] <= 14 and sub["n"] + sub["k"] <= 14
-                assert sub["m"] + sub["n"] + sub["k"] <= 17 and (op["threads"] == 1024) == any(
-                    q["m"] + q["n"] > 12 for q in op["micro"])
+                assert sub["m"] + sub["n"] + sub["k"] <= 17 and sub["k"] <= 4 and (op["threads"] == 1024) == any(
+                    q["m"] + q["n"] > 10 for q in op["micro"])
                 do(sub)
             return
         m, n, k = op["m"], op["n"], op["k"]
