@@ -174,6 +174,32 @@ def test_dag_schedule_orders_every_hazard(name, variant):
         assert max(depth) < len(ops) // 2, (max(depth), len(ops))
 
 
+@pytest.mark.parametrize("shape", ["random", "caterpillar", "balanced"])
+@pytest.mark.parametrize("seed", range(12))
+def test_random_networks_and_trees(seed, shape):
+    """Random closed networks, random trees of three shapes, random slicings, every combination of the
+    compiler's features: the compiled program (simulated in list order and in random DAG orders) equals the
+    plain numpy contraction of the network — exactly, the tensors hold small integers."""
+    from random_plans import make
+
+    rng = np.random.default_rng(1000 + seed)
+    n_tensors = int(rng.integers(3, 40))
+    n_edges = int(n_tensors * rng.uniform(1.0, 1.8))
+    groups = int(rng.integers(0, 4))
+    flat, want = make(seed, n_tensors=n_tensors, n_edges=n_edges, n_slice_groups=min(groups, n_edges), shape=shape)
+    for hoist in (True, False):
+        for microtree in (True, False):
+            for branches in (0, 1, 4):
+                cp = CompiledPlan(flat, hoist_invariant=hoist, use_microtree=microtree, dag_branches=branches)
+                desc = cp.describe()
+                assert run_program(desc, flat) == want, (hoist, microtree, branches)
+                if branches != 1:
+                    assert run_program(desc, flat, dag_seed=seed) == want, (hoist, microtree, branches)
+                if cp.num_slices >= 2:
+                    assert run_program(desc, flat, first=0, stride=2) + run_program(desc, flat, first=1, stride=2) == want
+                cp.close()
+
+
 def test_plan_errors():
     pp = load_golden("toy_path_lineflow")
     plan = pp.as_execution_plan()

@@ -130,6 +130,37 @@ def test_dag_schedule_is_bit_identical_to_post_order(name, variant):
         assert math.isclose(results[(0, 2)], want, rel_tol=REL)
 
 
+@pytest.mark.parametrize("shape", ["random", "caterpillar", "balanced"])
+@pytest.mark.parametrize("seed", range(12))
+def test_random_networks_and_trees(seed, shape):
+    """Random closed networks / trees / slicings (tests/random_plans.py; the CPU suite runs the same cases
+    through the program simulator): the CUDA path equals the plain numpy contraction exactly (small-integer
+    tensors), with every executor feature on and off, as stream launches and as graphs."""
+    from random_plans import make
+    from tensororder_b200.api import CompiledPlan
+
+    rng = np.random.default_rng(1000 + seed)
+    n_tensors = int(rng.integers(3, 40))
+    n_edges = int(n_tensors * rng.uniform(1.0, 1.8))
+    groups = int(rng.integers(0, 4))
+    flat, want = make(seed, n_tensors=n_tensors, n_edges=n_edges, n_slice_groups=min(groups, n_edges), shape=shape)
+    for kw in ({}, {"use_graph": 1}, {"use_graph": 0, "dag_branches": 1}, {"use_microtree": False},
+               {"hoist_invariant": False, "use_graph": 1}, {"kernel_policy": 1, "dag_branches": 5}):
+        cp = CompiledPlan(flat, **kw)
+        cp.upload()
+        assert cp.run() == want, kw
+        assert cp.run() == want, kw  # replay (graph instantiated on the second run in auto mode)
+        if cp.num_slices >= 2:
+            assert cp.run(first=0, stride=2) + cp.run(first=1, stride=2) == want, kw
+        cp.close()
+    flat_w, want_w = make(seed, n_tensors=n_tensors, n_edges=n_edges, n_slice_groups=min(groups, n_edges), shape=shape,
+                          integer=False)
+    cp = CompiledPlan(flat_w)
+    cp.upload()
+    assert math.isclose(cp.run(), want_w, rel_tol=REL)
+    cp.close()
+
+
 @pytest.mark.parametrize("name", [n for n in ALL if "count" not in load_golden(n).expected])
 def test_large_instances_slicing_invariance(name):
     """No reference count is stored for the largest family members (numpy needs minutes and tens of
