@@ -777,18 +777,87 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 // so a __syncthreads between joins is the only synchronisation.  Replaces hundreds of launch-bound
 // kernel launches per slice by one.
 // ------------------------------------------------------------------------------------------------
+// One join of a micro stage, for the thread's NU outputs  c0, c0 + NT, ...  (NU = 1 when the join has at most
+// NT outputs, so small joins carry no dead work).  AG / BG: the operand comes from global memory (L2, .cg
+// loads) rather than shared memory.  The loads of all NU outputs are issued before the first FMA.
+template <int NT, int LOG_NT, int NU, bool AG, bool BG>
+__device__ __forceinline__ void micro_join(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                                           double* __restrict__ mine, bool fwd_out, unsigned mask, int tot, int k,
+                                           unsigned mi_lo, unsigned ni_lo, int im_lo, int in_lo, double modp, double inv) {
+    const unsigned outs = 1u << tot;
+    for (unsigned c0 = threadIdx.x; c0 < outs; c0 += NT * NU) {
+        const double* ar[NU];
+        const double* br[NU];
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const unsigned c = c0 + u * NT;  // < outs: outs is a multiple of NT * NU whenever NU > 1
+            unsigned mi = mi_lo, ni = ni_lo;
+            int im = im_lo, in = in_lo;
+            for (int b = LOG_NT; b < tot; b++) {
+                const unsigned bit = (c >> b) & 1u;
+                if ((mask >> b) & 1u) { mi |= bit << im; im++; }
+                else { ni |= bit << in; in++; }
+            }
+            ar[u] = A + ((size_t)mi << k);
+            br[u] = B + ((size_t)ni << k);
+        }
+        double s[NU];
+        if (k == 0) {
+            double x[NU], y[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) x[u] = AG ? __ldcg(ar[u]) : ar[u][0];
+#pragma unroll
+            for (int u = 0; u < NU; u++) y[u] = BG ? __ldcg(br[u]) : br[u][0];
+#pragma unroll
+            for (int u = 0; u < NU; u++) s[u] = x[u] * y[u];
+        } else {
+            const int K2 = 1 << (k - 1);  // k <= 4 for mini joins: at most 8 double2 steps
+            double s0[NU], s1[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) s0[u] = s1[u] = 0.0;
+            for (int j = 0; j < K2; j++) {
+                double2 x[NU], y[NU];
+#pragma unroll
+                for (int u = 0; u < NU; u++)
+                    x[u] = AG ? __ldcg(reinterpret_cast<const double2*>(ar[u]) + j) : reinterpret_cast<const double2*>(ar[u])[j];
+#pragma unroll
+                for (int u = 0; u < NU; u++)
+                    y[u] = BG ? __ldcg(reinterpret_cast<const double2*>(br[u]) + j) : reinterpret_cast<const double2*>(br[u])[j];
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    s0[u] = fma(x[u].x, y[u].x, s0[u]);
+                    s1[u] = fma(x[u].y, y[u].y, s1[u]);
+                }
+                if (modp > 0.0 && (j & 63) == 63) {  // exact mode: reduce before 65 products pile up
+#pragma unroll
+                    for (int u = 0; u < NU; u++) {
+                        s0[u] = mod_reduce(s0[u], modp, inv);
+                        s1[u] = mod_reduce(s1[u], modp, inv);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; u++) s[u] = s0[u] + s1[u];
+        }
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const unsigned c = c0 + u * NT;
+            const double v = modp > 0.0 ? mod_reduce(s[u], modp, inv) : s[u];
+            C[c] = v;
+            if (fwd_out) mine[c] = v;
+        }
+    }
+}
+
 // Shared memory: [join descriptors | leaf cache | two forward buffers].  The serial chain of joins a CTA
 // walks is latency-bound: with the descriptors and the (tiny) leaf operands staged up front and each
 // result handed to the next join through the forward buffer, the critical path of a join is shared-memory
-// latency instead of two L2 round trips (store result, load it back).  Operands that do come from global
-// memory are fetched for U = 4 outputs at a time, so a thread has 8 independent L2 requests in flight
-// instead of one dependent round trip per output; the address bits of an output that come from the thread
-// index are decoded once per join, only the few bits above log2(NT) per output.
+// latency instead of two L2 round trips (store result, load it back).  The address bits of an output that
+// come from the thread index are decoded once per join, only the few bits above log2(NT) per output.
 template <int NT, int FWD>
 __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start,
                                                   const double* leaves, double* arena, const double* arena0,
                                                   const long long* leaf_off, int smem_ops, double modp) {
-    constexpr int U = 4;
     constexpr int LOG_NT = NT == 1024 ? 10 : 8;
     static_assert(NT == (1 << LOG_NT), "NT");
     extern __shared__ __align__(16) unsigned char micro_smem[];
@@ -822,90 +891,42 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
         const int a_src = staged ? op.a_src : 0, b_src = staged ? op.b_src : 0;
         const double* prev = fwd + ((i - first + 1) & 1) * FWD;  // written by join i-1
         double* mine = fwd + ((i - first) & 1) * FWD;
-        const double* A = a_src == 1 ? prev : a_src == 2 ? cache + op.a_soff
-                          : (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
-                                (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
-        const double* B = b_src == 1 ? prev : b_src == 2 ? cache + op.b_soff
-                          : (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
-                                (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
-        double* C = arena + op.c_off;
         const int tot = op.m + op.n, k = op.k;
-        const unsigned outs = 1u << tot;
-        const unsigned mask = op.mask_m;
-        const bool fwd_out = staged && op.fwd_out;
-        const bool a_glob = a_src == 0, b_glob = b_src == 0;
-        // address bits supplied by the thread index: decoded once per join
-        unsigned mi_lo = 0, ni_lo = 0;
-        int im_lo = 0, in_lo = 0;
-        const int lo_bits = tot < LOG_NT ? tot : LOG_NT;
-        for (int b = 0; b < lo_bits; b++) {
-            const unsigned bit = (threadIdx.x >> b) & 1u;
-            if ((mask >> b) & 1u) { mi_lo |= bit << im_lo; im_lo++; }
-            else { ni_lo |= bit << in_lo; in_lo++; }
-        }
-        for (unsigned c0 = threadIdx.x; c0 < outs; c0 += NT * U) {
-            const double* ar[U];
-            const double* br[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned c = c0 + u * NT;
-                unsigned mi = mi_lo, ni = ni_lo;
-                int im = im_lo, in = in_lo;
-                for (int b = LOG_NT; b < tot; b++) {
-                    const unsigned bit = (c >> b) & 1u;
-                    if ((mask >> b) & 1u) { mi |= bit << im; im++; }
-                    else { ni |= bit << in; in++; }
-                }
-                const bool ok = c < outs;  // rows of a dead slot point at row 0: loaded, never stored
-                ar[u] = A + (ok ? ((size_t)mi << k) : 0);
-                br[u] = B + (ok ? ((size_t)ni << k) : 0);
+        if (threadIdx.x < (1u << tot)) {  // warps without an output go straight to the barrier
+            const double* A = a_src == 1 ? prev : a_src == 2 ? cache + op.a_soff
+                              : (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
+                                    (op.a_leaf >= 0 ? leaf_off[op.a_leaf] : 0);
+            const double* B = b_src == 1 ? prev : b_src == 2 ? cache + op.b_soff
+                              : (op.b_space == 0 ? leaves : (op.b_space == 2 ? arena0 : arena)) + op.b_off +
+                                    (op.b_leaf >= 0 ? leaf_off[op.b_leaf] : 0);
+            double* C = arena + op.c_off;
+            const unsigned mask = op.mask_m;
+            const bool fwd_out = staged && op.fwd_out;
+            // address bits supplied by the thread index: decoded once per join
+            unsigned mi_lo = 0, ni_lo = 0;
+            int im_lo = 0, in_lo = 0;
+            const int lo_bits = tot < LOG_NT ? tot : LOG_NT;
+            for (int b = 0; b < lo_bits; b++) {
+                const unsigned bit = (threadIdx.x >> b) & 1u;
+                if ((mask >> b) & 1u) { mi_lo |= bit << im_lo; im_lo++; }
+                else { ni_lo |= bit << in_lo; in_lo++; }
             }
-            double s[U];
-            if (k == 0) {
-                double x[U], y[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) x[u] = a_glob ? __ldcg(ar[u]) : ar[u][0];
-#pragma unroll
-                for (int u = 0; u < U; u++) y[u] = b_glob ? __ldcg(br[u]) : br[u][0];
-#pragma unroll
-                for (int u = 0; u < U; u++) s[u] = x[u] * y[u];
-            } else {
-                const int K2 = 1 << (k - 1);
-                double s0[U], s1[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) s0[u] = s1[u] = 0.0;
-                for (int j = 0; j < K2; j++) {
-                    double2 x[U], y[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        x[u] = a_glob ? __ldcg(reinterpret_cast<const double2*>(ar[u]) + j) : reinterpret_cast<const double2*>(ar[u])[j];
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        y[u] = b_glob ? __ldcg(reinterpret_cast<const double2*>(br[u]) + j) : reinterpret_cast<const double2*>(br[u])[j];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        s0[u] = fma(x[u].x, y[u].x, s0[u]);
-                        s1[u] = fma(x[u].y, y[u].y, s1[u]);
-                    }
-                    if (modp > 0.0 && (j & 63) == 63) {  // exact mode: reduce before 65 products pile up
-#pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            s0[u] = mod_reduce(s0[u], modp, inv);
-                            s1[u] = mod_reduce(s1[u], modp, inv);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) s[u] = s0[u] + s1[u];
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned c = c0 + u * NT;
-                if (c >= outs) continue;
-                const double v = modp > 0.0 ? mod_reduce(s[u], modp, inv) : s[u];
-                C[c] = v;
-                if (fwd_out) mine[c] = v;
-            }
+            const int nu = tot <= LOG_NT ? 1 : (tot == LOG_NT + 1 ? 2 : 4);
+            const int sel = (a_src == 0 ? 2 : 0) | (b_src == 0 ? 1 : 0);
+#define TOB_MICRO_CALL(NU, AG, BG) \
+    micro_join<NT, LOG_NT, NU, AG, BG>(A, B, C, mine, fwd_out, mask, tot, k, mi_lo, ni_lo, im_lo, in_lo, modp, inv)
+#define TOB_MICRO_SEL(NU)                                    \
+    switch (sel) {                                           \
+        case 0: TOB_MICRO_CALL(NU, false, false); break;     \
+        case 1: TOB_MICRO_CALL(NU, false, true); break;      \
+        case 2: TOB_MICRO_CALL(NU, true, false); break;      \
+        default: TOB_MICRO_CALL(NU, true, true); break;      \
+    }
+            if (nu == 1) { TOB_MICRO_SEL(1) }
+            else if (nu == 2) { TOB_MICRO_SEL(2) }
+            else { TOB_MICRO_SEL(4) }
+#undef TOB_MICRO_SEL
+#undef TOB_MICRO_CALL
         }
         __syncthreads();
     }
