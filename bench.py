@@ -202,7 +202,20 @@ def b200_arm(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation (NCCL_DEBUG=VERSION/INFO): keep
+        # stdout for the one JSON line by pointing fd 1 at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     items = load_workload(args.min_n, args.max_n, args.workload, args.slice_bits)
     n_inst = len(items)
 
