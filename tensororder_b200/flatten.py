@@ -88,6 +88,14 @@ class _LeafArena:
         return offset
 
 
+try:  # the compiled loop (tensororder_b200/_flatten_fast.pyx, built by tensororder_b200.build); same logic as below
+    from . import _flatten_fast
+except ImportError:  # not built: the Python loop below does the same work
+    _flatten_fast = None
+
+USE_COMPILED = True  # tests flip this to run both implementations
+
+
 def flatten_plan(plan, tensor_factory=None) -> FlatPlan:
     network = plan.network
     # edge id -> slice group index (non-empty groups only, in order)
@@ -99,6 +107,11 @@ def flatten_plan(plan, tensor_factory=None) -> FlatPlan:
         for e in group:
             group_of[int(e)] = n_groups
         n_groups += 1
+    if _flatten_fast is not None and USE_COMPILED and tensor_factory is None:
+        (nl, nr, nf, lr, lo, ast, ae, data, lti) = _flatten_fast.flatten_tree(plan, group_of)
+        return FlatPlan(node_left=nl, node_right=nr, node_leaf=nf, leaf_rank=lr, leaf_data_offset=lo,
+                        leaf_axis_start=ast, leaf_axis_edge=ae, leaf_data=data, n_slice_groups=n_groups,
+                        leaf_tensor_index=lti)
 
     node_left: List[int] = []
     node_right: List[int] = []

@@ -200,6 +200,63 @@ def test_random_networks_and_trees(seed, shape):
                 cp.close()
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_compiled_flatten_equals_python_flatten(name):
+    """`flatten_plan` has its hot loop twice: tensororder_b200/_flatten_fast.pyx (Cython, built in-tree) and the
+    Python loop it was written from.  Same arrays, bit for bit, on every fixture and variant."""
+    from tensororder_b200 import flatten
+
+    assert flatten._flatten_fast is not None, "python -m tensororder_b200.build builds _flatten_fast"
+    pp = load_golden(name)
+    for v in [None] + list(range(len(pp.variants))):
+        plan = (pp if v is None else pp.variant(v)).as_execution_plan()
+        try:
+            flatten.USE_COMPILED = True
+            a = flatten.flatten_plan(plan)
+            flatten.USE_COMPILED = False
+            b = flatten.flatten_plan(plan)
+        finally:
+            flatten.USE_COMPILED = True
+        for fld in ("node_left", "node_right", "node_leaf", "leaf_rank", "leaf_data_offset", "leaf_axis_start",
+                    "leaf_axis_edge", "leaf_data"):
+            x, y = getattr(a, fld), getattr(b, fld)
+            assert x.dtype == y.dtype and np.array_equal(x, y), fld
+        assert a.leaf_tensor_index == b.leaf_tensor_index and a.n_slice_groups == b.n_slice_groups
+
+
+def test_compiled_flatten_error_paths_and_foreign_arrays():
+    from tensororder_b200 import flatten
+    from tensororder_b200.plan_format import PlanNetwork, PlanTensor, PlanTree, StoredExecutionPlan
+
+    class OwnArray(PlanTensor):  # build() that ignores the factory's buffer (allowed by the reference interface)
+        def build(self, tensor_factory):
+            return np.array(self._data, dtype=np.float32)
+
+    for cls in (PlanTensor, OwnArray):
+        tensors = [cls((2, 2), [[1, 2], [3, 4]], False, "a"), cls((2, 2), [[1, 0], [0, 1]], False, "b")]
+        net = PlanNetwork(tensors, [[0, 1], [0, 1]], [[0, 1], [0, 1]])
+        plan = StoredExecutionPlan(PlanTree([("leaf", 0), ("leaf", 1), ("join", 0, 1)]), net, [])
+        for compiled in (True, False):
+            flatten.USE_COMPILED = compiled
+            try:
+                f = flatten.flatten_plan(plan)
+            finally:
+                flatten.USE_COMPILED = True
+            assert f.leaf_data.tolist() == [1, 2, 3, 4, 1, 0, 0, 1] and f.node_left.tolist() == [-1, -1, 0]
+    bad = StoredExecutionPlan(PlanTree([("leaf", 0), ("leaf", 1)]), net, [])  # two roots
+    dangling = StoredExecutionPlan(PlanTree([("leaf", 0), ("leaf", 1), ("join", 0, 1)]),
+                                   PlanNetwork(tensors, [[0, -1], [0, 1]], [[0, 1], [0, 1]]), [])
+    for compiled in (True, False):
+        flatten.USE_COMPILED = compiled
+        try:
+            with pytest.raises(ValueError, match="single rooted tree"):
+                flatten.flatten_plan(bad)
+            with pytest.raises(ValueError, match="dangling"):
+                flatten.flatten_plan(dangling)
+        finally:
+            flatten.USE_COMPILED = True
+
+
 def test_plan_errors():
     pp = load_golden("toy_path_lineflow")
     plan = pp.as_execution_plan()
