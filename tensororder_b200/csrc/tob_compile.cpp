@@ -17,6 +17,7 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <chrono>
 
 #include "tob_internal.h"
 
@@ -293,6 +294,15 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     P->src_leaf_len = d->leaf_data_len;
     const int S = d->n_slice_groups;
 
+    static const bool trace_compile = getenv("TOB_TRACE_COMPILE") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tmark = tnow();
+    auto lap = [&](const char* what) {
+        if (!trace_compile) return;
+        const double t = tnow();
+        fprintf(stderr, "[tob compile] %-28s %8.1f us\n", what, t - tmark);
+        tmark = t;
+    };
     // ---- leaves ----
     P->leaves.resize(d->n_leaves);
     for (int l = 0; l < d->n_leaves; l++) {
@@ -308,6 +318,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             if (e < 0 && -(e + 1) >= S) return fail("leaf axis names a slice group that does not exist");
     }
 
+    lap("leaves");
     // ---- nodes: structure + edge sets (bottom-up) ----
     const int N = d->n_nodes;
     P->nodes.assign(N, NodeInfo());
@@ -348,6 +359,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     if (!P->nodes[N - 1].edges.empty())
         return fail("root tensor is not rank 0 (the network has open indices)");
 
+    lap("nodes + edge sets");
     // ---- canonical layouts (top-down) ----
     int32_t max_edge = -1;
     for (const NodeInfo& X : P->nodes)
@@ -374,6 +386,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         }
     }
 
+    lap("layouts");
     // ---- leaves: device placement, upload permutation, slice terms ----
     int64_t leaf_top = 0;
     for (int i = 0; i < N; i++) {
@@ -407,6 +420,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     }
     P->leaf_doubles = leaf_top;
 
+    lap("leaf placement");
     // ---- ops (post-order), micro subtrees, hoisting, arena ----
     const bool hoist = opt.hoist_invariant && S > 0;
     const int max_branches = opt.dag_branches == 0 ? 16 : opt.dag_branches;
@@ -578,12 +592,14 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         for (int i = 0; i < N; i++)
             if (P->nodes[i].leaf < 0 && !mini[i] && phase[i] == dep && lvl[i] == level) emit(i, list);
     };
+    lap("levels");
     for (int dep = hoist ? 0 : 1; dep <= 1; dep++) {
         int max_level = -1;
         for (int i = 0; i < N; i++)
             if (P->nodes[i].leaf < 0 && phase[i] == dep) max_level = std::max(max_level, lvl[i]);
         for (int level = 0; level <= max_level; level++) run_stage(dep, level, dep ? &P->slice_ops : &P->invariant_ops);
     }
+    lap("stages: ops + arena");
     P->root = P->nodes[N - 1].where;
     Op acc;
     acc.kind = OP_ACCUM;
@@ -598,6 +614,7 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     const bool cheap = (P->arena_doubles + P->ws_doubles) * 8 <= ((int64_t)2 << 30);
     P->lanes = (S > 0 && (want_lanes == 2 || (want_lanes == 0 && cheap))) ? 2 : 1;
     P->branches = std::max(schedule_branches(&P->invariant_ops, max_branches), schedule_branches(&P->slice_ops, max_branches));
+    lap("dag schedule");
     return TOB_OK;
 }
 
