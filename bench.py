@@ -145,9 +145,24 @@ def cpu_threads():
     return os.cpu_count() or 1
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin OpenBLAS to one thread; the
+    reference's numpy path gets every core the box has (OpenBLAS caps at its build maximum)."""
+    import numpy  # noqa: F401
+
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
+
+
 def run_cpu_sample(items):
     """The reference's numpy path (oracle port) over `items`; returns seconds and counts."""
     from oracle import numpy_oracle
+
+    use_all_cores()
 
     t0 = time.perf_counter()
     counts = [float(numpy_oracle.contract_sliced(it["pp"].to_json())) for it in items]
@@ -157,7 +172,7 @@ def run_cpu_sample(items):
 def reference_arm(args, rank):
     if rank != 0:
         return  # under torchrun only rank 0 runs the CPU arm
-    import numpy  # noqa: F401  (all host cores: OpenBLAS default threading)
+    use_all_cores()
 
     items = [it for it in load_workload(args.min_n, args.max_n) if it["n"] <= args.cpu_max_n]
     n_workload = len(items)
