@@ -86,6 +86,7 @@ struct tob_plan {
     int64_t last_gemm_launches = 0;
     double slice_flops = 0, invariant_flops = 0;
     bool time_gemm = false;
+    bool in_flight = false;  // a run or profile pass has been issued and not yet waited for
     double modulus = 0.0;  // exact mode: prime modulus (< 2^23), 0 = float64 arithmetic
 };
 
@@ -321,9 +322,13 @@ int64_t tob_plan_num_ops(const tob_plan* p) { return (int64_t)(p->prog.invariant
 static void release_lanes(tob_plan* p) {
     for (int l = 0; l < kMaxLanes; l++) {
         Lane& L = p->lane[l];
-        if (L.own_stream) cudaStreamSynchronize(L.own_stream);
-        for (int b = 1; b < L.n_branches; b++)
-            if (L.branch_stream[b]) cudaStreamSynchronize(L.branch_stream[b]);
+        // a completed run has joined every branch into the lane's stream and waited for it: only a run that
+        // failed half-way can have left work behind
+        if (p->in_flight) {
+            if (L.own_stream) cudaStreamSynchronize(L.own_stream);
+            for (int b = 1; b < L.n_branches; b++)
+                if (L.branch_stream[b]) cudaStreamSynchronize(L.branch_stream[b]);
+        }
         if (L.graph_exec) cudaGraphExecDestroy(L.graph_exec);
         if (L.graph) cudaGraphDestroy(L.graph);
         if (L.inv_graph_exec) cudaGraphExecDestroy(L.inv_graph_exec);
@@ -557,8 +562,10 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
     }
     const double t_fill = now_ms();
     // ---- ONE pinned host->device copy: state, tables, micro programs, leaves ----
+    p->in_flight = true;
     CUDA_TRY(cudaMemcpyAsync(p->d_block, p->h_block, prefix_bytes, cudaMemcpyHostToDevice, p->lane[0].stream));
     CUDA_TRY(cudaStreamSynchronize(p->lane[0].stream));
+    p->in_flight = false;
     if (trace)
         fprintf(stderr, "[tob] upload: ensure_device %.3f  streams+tables %.3f  alloc %.3f  fill %.3f  h2d+sync %.3f ms (%zu B)\n",
                 t_dev - t_begin, t_tables - t_dev, t_alloc - t_tables, t_fill - t_alloc, now_ms() - t_fill, prefix_bytes);
@@ -730,6 +737,7 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
                               !(p->time_gemm && inv_has_gemm) && !p->prog.invariant_ops.empty();
 
     const double t_issue0 = now_ms();
+    p->in_flight = true;
     CUDA_TRY(cudaEventRecord(L0.ev_a, L0.stream));
     uint64_t done = 0;
     bool first_batch = true;
@@ -821,6 +829,7 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     p->last_gemm_launches = (int64_t)n_gemm;
     *result = *p->h_readback;
     p->runs++;
+    p->in_flight = false;
     return TOB_OK;
 }
 
@@ -872,6 +881,7 @@ int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_op
     if (rc != TOB_OK) return rc;
     int launches = 0;
     Lane& L0 = p->lane[0];
+    p->in_flight = true;
     p->h_state[0].next_slice = slice;
     p->h_state[0].stride = 1;
     p->h_state[0].slot = 0;
@@ -898,6 +908,7 @@ int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_op
     for (int64_t j = 0; j < n_ops; j++) CUDA_TRY(cudaEventElapsedTime(&ms_per_op[j], ev[j], ev[j + 1]));
     for (auto& e : ev) cudaEventDestroy(e);
     if (result) *result = *p->h_readback;
+    p->in_flight = false;
     return TOB_OK;
 }
 
