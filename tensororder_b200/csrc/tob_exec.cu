@@ -839,6 +839,15 @@ int tob_plan_set_modulus(tob_plan* p, double modulus) {
         set_error("modulus must be 0 or an integer in [2, 2^23)");
         return TOB_E_INVALID;
     }
+    if (modulus != p->modulus) {  // captured graphs carry the modulus in their kernel parameters
+        for (int l = 0; l < kMaxLanes; l++) {
+            Lane& L = p->lane[l];
+            if (L.graph_exec) { cudaGraphExecDestroy(L.graph_exec); L.graph_exec = nullptr; }
+            if (L.graph) { cudaGraphDestroy(L.graph); L.graph = nullptr; }
+            if (L.inv_graph_exec) { cudaGraphExecDestroy(L.inv_graph_exec); L.inv_graph_exec = nullptr; }
+            if (L.inv_graph) { cudaGraphDestroy(L.inv_graph); L.inv_graph = nullptr; }
+        }
+    }
     p->modulus = modulus;
     return TOB_OK;
 }

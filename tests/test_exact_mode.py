@@ -94,3 +94,31 @@ def test_exact_counts_beyond_the_reference(name):
     assert api.last_stats["exact_passes"] >= math.ceil(math.log2(exact) / 23)
     if name == "vc200_lineflow":
         assert api.contract_sliced(pp.variant("min3").as_execution_plan()) == exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,variant", [("vc100_lineflow", None), ("vc100_lineflow", "min4")])
+def test_modulus_change_on_a_resident_plan(name, variant):
+    """A resident plan whose slices (and slice-invariant prologue) replay as CUDA graphs: the graphs carry the
+    modulus in their kernel parameters, so changing it must re-capture them.  0/1 leaves are residues for every
+    prime, so the same upload serves all passes."""
+    from tensororder_b200.api import CompiledPlan, EXACT_PRIMES
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name)
+    want = int(pp.expected["count_exact"])
+    if variant:
+        pp = pp.variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    for graph in (1, 2, 0):
+        cp = CompiledPlan(flat, use_graph=graph)
+        cp.upload()
+        for p in (EXACT_PRIMES[0], EXACT_PRIMES[1], 0, EXACT_PRIMES[2]):
+            cp.set_modulus(p)
+            for _ in range(3):  # auto mode switches to graph replay on the second run
+                got = cp.run()
+                if p:
+                    assert got == want % p, (graph, p, got, want % p)
+                else:
+                    assert math.isclose(got, float(want), rel_tol=1e-12)
+        cp.close()
