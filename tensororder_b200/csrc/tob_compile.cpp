@@ -572,9 +572,13 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
                 bins[best].push_back(j);
                 load[best] += work[j];
             }
+            mp.cta_start.reserve(n_cta + 1);
+            size_t n_mini = 0;
+            for (const auto& fr : frags) n_mini += fr.size();
+            mp.ops.reserve(n_mini);
             mp.cta_start.push_back(0);
             for (int c = 0; c < n_cta; c++) {
-                std::sort(bins[c].begin(), bins[c].end());  // fragments of one stage are independent; keep tree order
+                if (bins[c].size() > 1) std::sort(bins[c].begin(), bins[c].end());  // chains of one stage are independent; keep tree order
                 for (size_t j : bins[c])
                     for (const Op& op : frags[j]) mp.ops.push_back(op);
                 mp.cta_start.push_back((int32_t)mp.ops.size());
@@ -593,6 +597,8 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             if (P->nodes[i].leaf < 0 && !mini[i] && phase[i] == dep && lvl[i] == level) emit(i, list);
     };
     lap("levels");
+    P->invariant_ops.reserve(hoist ? N / 4 + 8 : 0);
+    P->slice_ops.reserve(N / 4 + 8);
     for (int dep = hoist ? 0 : 1; dep <= 1; dep++) {
         int max_level = -1;
         for (int i = 0; i < N; i++)

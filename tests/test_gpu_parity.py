@@ -264,3 +264,44 @@ def test_out_of_memory_maps_to_reference_error():
     with pytest.raises(OutOfMemoryError):
         cp.upload()
     cp.close()
+
+
+@pytest.mark.parametrize("name,variant", [("vc150_lineflow", None), ("vc200_lineflow", "min3"), ("vc220_lineflow", None)])
+def test_count_is_multilinear_in_a_variable_weight(name, variant):
+    """Size-independent property at BASELINE sizes (no reference count needed): the weighted count is linear in
+    the weight pair of every variable, Z(w-, w+) = w- * Z(x=0) + w+ * Z(x=1).  A variable's leaf is the copy
+    tensor diag(w-, w+) (VariableTensor.build, tensor_network_constructions.py:144-152): rewrite it in the
+    flat plan's leaf buffer and contract three times."""
+    import dataclasses
+
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name)
+    if variant:
+        pp = pp.variant(variant)
+    flat = flatten_plan(pp.as_execution_plan())
+    rng = np.random.default_rng(7)
+    picked = 0
+    for leaf in rng.permutation(flat.n_leaves):
+        r = int(flat.leaf_rank[leaf])
+        off = int(flat.leaf_data_offset[leaf])
+        d = flat.leaf_data[off: off + (1 << r)]
+        if r < 2 or np.count_nonzero(d) != 2 or d[0] != 1.0 or d[-1] != 1.0:
+            continue  # not a copy tensor
+        results = {}
+        for w in ((1.0, 0.0), (0.0, 1.0), (0.375, 1.75)):
+            data = flat.leaf_data.copy()
+            data[off], data[off + (1 << r) - 1] = w
+            cp = CompiledPlan(dataclasses.replace(flat, leaf_data=data))
+            cp.upload()
+            results[w] = cp.run()
+            cp.close()
+        z0, z1, z = results[(1.0, 0.0)], results[(0.0, 1.0)], results[(0.375, 1.75)]
+        assert z0 >= 0 and z1 > 0
+        assert math.isclose(z, 0.375 * z0 + 1.75 * z1, rel_tol=REL), (leaf, z, z0, z1)
+        assert math.isclose(z0 + z1, load_golden(name).expected["count"], rel_tol=REL)
+        picked += 1
+        if picked == 2:
+            break
+    assert picked == 2
