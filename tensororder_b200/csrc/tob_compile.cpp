@@ -558,7 +558,9 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
         if (!frags.empty()) {
             P->micro.emplace_back();
             MicroProgram& mp = P->micro.back();
-            mp.threads = max_outs_log2 > 10 ? 1024 : 256;
+            static const int force_threads = getenv("TOB_MICRO_THREADS") ? atoi(getenv("TOB_MICRO_THREADS")) : 0;  // experiments
+            static const int big_from = getenv("TOB_MICRO_BIG_FROM") ? atoi(getenv("TOB_MICRO_BIG_FROM")) : 10;
+            mp.threads = force_threads == 256 || force_threads == 1024 ? force_threads : (max_outs_log2 > big_from ? 1024 : 256);
             const int n_cta = (int)std::min<size_t>(frags.size(), 2 * kNumSMs);
             std::vector<size_t> order(frags.size());
             for (size_t j = 0; j < order.size(); j++) order[j] = j;
