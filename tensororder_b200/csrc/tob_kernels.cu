@@ -783,7 +783,8 @@ cudaError_t launch_final_sum(double* acc, const double* results, int count, doub
 template <int NT, int LOG_NT, int NU, bool AG, bool BG>
 __device__ __forceinline__ void micro_join(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                                            double* __restrict__ mine, bool fwd_out, unsigned mask, int tot, int k,
-                                           unsigned mi_lo, unsigned ni_lo, int im_lo, int in_lo, double modp, double inv) {
+                                           unsigned mi_lo, unsigned ni_lo, const uint2* __restrict__ hi_tab, double modp,
+                                           double inv) {
     const unsigned outs = 1u << tot;
     for (unsigned c0 = threadIdx.x; c0 < outs; c0 += NT * NU) {
         const double* ar[NU];
@@ -791,15 +792,10 @@ __device__ __forceinline__ void micro_join(const double* __restrict__ A, const d
 #pragma unroll
         for (int u = 0; u < NU; u++) {
             const unsigned c = c0 + u * NT;  // < outs: outs is a multiple of NT * NU whenever NU > 1
-            unsigned mi = mi_lo, ni = ni_lo;
-            int im = im_lo, in = in_lo;
-            for (int b = LOG_NT; b < tot; b++) {
-                const unsigned bit = (c >> b) & 1u;
-                if ((mask >> b) & 1u) { mi |= bit << im; im++; }
-                else { ni |= bit << in; in++; }
-            }
-            ar[u] = A + ((size_t)mi << k);
-            br[u] = B + ((size_t)ni << k);
+            // the bits above log2(NT) were decoded once per join into hi_tab (<= 16 entries)
+            const uint2 hi = NU > 1 ? hi_tab[c >> LOG_NT] : make_uint2(0u, 0u);
+            ar[u] = A + ((size_t)(mi_lo | hi.x) << k);
+            br[u] = B + ((size_t)(ni_lo | hi.y) << k);
         }
         double s[NU];
         if (k == 0) {
@@ -860,6 +856,7 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
                                                   const long long* leaf_off, int smem_ops, double modp) {
     constexpr int LOG_NT = NT == 1024 ? 10 : 8;
     static_assert(NT == (1 << LOG_NT), "NT");
+    __shared__ uint2 hi_tab[64];  // 2^(14 - 8) entries at most
     extern __shared__ __align__(16) unsigned char micro_smem[];
     MicroOpDev* sops = reinterpret_cast<MicroOpDev*>(micro_smem);
     double* cache = reinterpret_cast<double*>(micro_smem + (size_t)smem_ops * sizeof(MicroOpDev));
@@ -892,6 +889,20 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
         const double* prev = fwd + ((i - first + 1) & 1) * FWD;  // written by join i-1
         double* mine = fwd + ((i - first) & 1) * FWD;
         const int tot = op.m + op.n, k = op.k;
+        if (tot > LOG_NT) {  // decode the (at most 4) output-index bits above log2(NT) once: hi_tab[c >> LOG_NT]
+            if (threadIdx.x < (1u << (tot - LOG_NT))) {
+                const unsigned maskv = op.mask_m;
+                int im = __popc(maskv & ((1u << LOG_NT) - 1u)), in = LOG_NT - im;  // bits the low part already used
+                unsigned mi = 0, ni = 0;
+                for (int b = LOG_NT; b < tot; b++) {
+                    const unsigned bit = (threadIdx.x >> (b - LOG_NT)) & 1u;
+                    if ((maskv >> b) & 1u) { mi |= bit << im; im++; }
+                    else { ni |= bit << in; in++; }
+                }
+                hi_tab[threadIdx.x] = make_uint2(mi, ni);
+            }
+            __syncthreads();
+        }
         if (threadIdx.x < (1u << tot)) {  // warps without an output go straight to the barrier
             const double* A = a_src == 1 ? prev : a_src == 2 ? cache + op.a_soff
                               : (op.a_space == 0 ? leaves : (op.a_space == 2 ? arena0 : arena)) + op.a_off +
@@ -914,7 +925,7 @@ __global__ void __launch_bounds__(NT) k_microtree(const MicroOpDev* __restrict__
             const int nu = tot <= LOG_NT ? 1 : (tot == LOG_NT + 1 ? 2 : 4);
             const int sel = (a_src == 0 ? 2 : 0) | (b_src == 0 ? 1 : 0);
 #define TOB_MICRO_CALL(NU, AG, BG) \
-    micro_join<NT, LOG_NT, NU, AG, BG>(A, B, C, mine, fwd_out, mask, tot, k, mi_lo, ni_lo, im_lo, in_lo, modp, inv)
+    micro_join<NT, LOG_NT, NU, AG, BG>(A, B, C, mine, fwd_out, mask, tot, k, mi_lo, ni_lo, hi_tab, modp, inv)
 #define TOB_MICRO_SEL(NU)                                    \
     switch (sel) {                                           \
         case 0: TOB_MICRO_CALL(NU, false, false); break;     \
