@@ -451,6 +451,176 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant for SHORT K (K <= 2 * TK per split): a CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...
+// and its cp.async ring runs across tile boundaries, so the operands of the next tile(s) are in flight while
+// the current tile computes and scatters its 64 KB of output.  With one K step per tile the one-tile-per-CTA
+// kernel is a serial load -> DMMA -> store per CTA (two CTAs per SM are the only overlap): store-bound joins
+// (k <= 5) reach 0.65 of HBM there.  256 threads at two CTAs per SM leave 128 registers, so the extra tile
+// state costs no spills (the warp-specialised kernel at 320 threads has no such room: DESIGN.md §4).
+// ------------------------------------------------------------------------------------------------
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB>
+__global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NT = WM * WN * 32;
+    constexpr int WTM = TM / WM, WTN = TN / WN;
+    constexpr int MB = WTM / 8, NB = WTN / 8;
+    constexpr int LDS = TK + 4;
+    constexpr int CHUNKS = TK / 2;
+    constexpr int RPP = NT / CHUNKS;
+    constexpr int K4 = TK / 4;
+    static_assert(TM % RPP == 0 && TN % RPP == 0, "loader passes");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
+    unsigned long long* cN = cM + TM;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    const int k = p.k, ks = p.ksplit_log2;
+
+    for (int i = tid; i < TM; i += NT) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NT) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+
+    const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
+    const unsigned long long tiles = tilesM * tilesN;
+    const unsigned long long total = tiles << ks;
+    const unsigned long long group = tilesM < 16 ? tilesM : 16;
+    const unsigned long long per_group = group * tilesN;
+    const unsigned long long Ksplit = (1ull << k) >> ks;
+    const int KT = (int)((Ksplit + TK - 1) / TK);
+    const bool partial = Ksplit < (unsigned long long)TK;
+    const int k4_end = partial ? (int)((Ksplit + 3) / 4) : K4;
+    const unsigned long long nmine = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nsteps = (long long)nmine * KT;
+    const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
+
+    // same rasterisation as k_gemm_dmma: id -> (split, tile_m, tile_n); every count is a power of two
+    const int tiles_log2 = (p.m - TM_LOG2) + (p.n - TN_LOG2);
+    const int group_log2 = (p.m - TM_LOG2) < 4 ? (p.m - TM_LOG2) : 4;
+    const int pg_log2 = group_log2 + (p.n - TN_LOG2);
+    auto decode = [&](unsigned long long id, unsigned long long& split, unsigned long long& tile_m, unsigned long long& tile_n) {
+        split = id >> tiles_log2;
+        const unsigned long long tid_in = id & (tiles - 1);
+        const unsigned long long gidx = tid_in >> pg_log2, r = tid_in & (per_group - 1);
+        tile_m = (gidx << group_log2) + (r & (group - 1));
+        tile_n = r >> group_log2;
+    };
+
+    // ---- loader: runs STAGES-1 steps ahead of the math, across tile boundaries ----
+    const int chunk = tid % CHUNKS, row0 = tid / CHUNKS;
+    const unsigned long long pass_stride = (unsigned long long)RPP << k;
+    const int dst_off = row0 * LDS + chunk * 2;
+    unsigned long long l_id = blockIdx.x;
+    int l_kt = 0;
+    const double *a_src = nullptr, *b_src = nullptr;
+    auto set_load_tile = [&](unsigned long long id) {
+        unsigned long long split, tile_m, tile_n;
+        decode(id, split, tile_m, tile_n);
+        a_src = Abase + ((tile_m << TM_LOG2) << k) + split * Ksplit + ((unsigned long long)row0 << k) + chunk * 2;
+        b_src = Bbase + ((tile_n << TN_LOG2) << k) + split * Ksplit + ((unsigned long long)row0 << k) + chunk * 2;
+    };
+    auto load_step = [&](int s) {
+        double* as = As + s * TM * LDS + dst_off;
+        double* bs = Bs + s * TN * LDS + dst_off;
+        const double* ag = a_src + l_kt * TK;
+        const double* bg = b_src + l_kt * TK;
+        if (partial) {
+            const int nbytes = ((unsigned long long)(chunk * 2) < Ksplit) ? 16 : 0;
+            const int back = nbytes ? 0 : chunk * 2;
+#pragma unroll
+            for (int i = 0; i < TM / RPP; i++) cp_async16_zfill(as + i * RPP * LDS, ag + i * pass_stride - back, nbytes);
+#pragma unroll
+            for (int i = 0; i < TN / RPP; i++) cp_async16_zfill(bs + i * RPP * LDS, bg + i * pass_stride - back, nbytes);
+        } else {
+#pragma unroll
+            for (int i = 0; i < TM / RPP; i++) cp_async16(as + i * RPP * LDS, ag + i * pass_stride);
+#pragma unroll
+            for (int i = 0; i < TN / RPP; i++) cp_async16(bs + i * RPP * LDS, bg + i * pass_stride);
+        }
+        if (++l_kt == KT) {
+            l_kt = 0;
+            l_id += gridDim.x;
+            if (l_id < total) set_load_tile(l_id);
+        }
+    };
+
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; i++)
+#pragma unroll
+        for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (nmine > 0) set_load_tile(l_id);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nsteps) load_step(s);
+        cp_async_commit();
+    }
+    const int frag_off_a = (wm * WTM + g) * LDS + t;
+    const int frag_off_b = (wn * WTN + g) * LDS + t;
+    const bool vec = (p.mask_n & 1ull) != 0;
+    unsigned long long c_id = blockIdx.x;
+    int c_kt = 0;
+    double af[2][MB], bf[2][NB];
+    for (long long s = 0; s < nsteps; s++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const long long nk = s + STAGES - 1;
+        if (nk < nsteps) load_step((int)(nk % STAGES));
+        cp_async_commit();
+        const double* as = As + (int)(s % STAGES) * TM * LDS + frag_off_a;
+        const double* bs = Bs + (int)(s % STAGES) * TN * LDS + frag_off_b;
+#pragma unroll
+        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS];
+#pragma unroll
+        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS];
+#pragma unroll
+        for (int k4 = 0; k4 < K4; k4++) {
+            if (k4 >= k4_end) break;
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < K4) {
+#pragma unroll
+                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + (k4 + 1) * 4];
+#pragma unroll
+                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + (k4 + 1) * 4];
+            }
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+        if (++c_kt == KT) {
+            // ---- this tile is complete: scatter it (the loads of the next tiles are already in flight) ----
+            unsigned long long split, tile_m, tile_n;
+            decode(c_id, split, tile_m, tile_n);
+            double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
+            const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+#pragma unroll
+            for (int i = 0; i < MB; i++) {
+                const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
+#pragma unroll
+                for (int j = 0; j < NB; j++) {
+                    const int col = wn * WTN + j * 8 + 2 * t;
+                    if (vec) {
+                        *reinterpret_cast<double2*>(Cout + (rbase | cN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else {
+                        Cout[rbase | cN[col]] = acc[i][j][0];
+                        Cout[rbase | cN[col + 1]] = acc[i][j][1];
+                    }
+                    acc[i][j][0] = acc[i][j][1] = 0.0;
+                }
+            }
+            c_kt = 0;
+            c_id += gridDim.x;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Warp-specialised DMMA GEMM: one producer warp streams whole 128-byte operand rows into the padded
 // K-major tiles with bulk async copies (cp.async.bulk, SASS UBLKCP) that signal a per-stage "full"
 // mbarrier by transaction bytes; eight consumer warps wait on "full", run the DMMA steps, and arrive on
@@ -670,6 +840,7 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_77_C k_gemm_dmma<7, 7, 4, 4, 32, 3, 1>
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
+#define GEMM_76_P k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true, false>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true>
@@ -695,6 +866,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
@@ -999,6 +1172,7 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             // 2/3 = one producer warp (padded 3-stage / swizzled 4-stage ring); 1 = 128-byte bulk copies
             // (UBLKCP: 2.4x SLOWER, request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
             static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 4;
+            static const bool persist_small_k = !(getenv("TOB_GEMM_PERSIST") && atoi(getenv("TOB_GEMM_PERSIST")) == 0);
             if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
                 GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else if (ws == 4 && (op.k - op.ksplit_log2) >= 8)
@@ -1012,6 +1186,9 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 GEMM_76_WZ<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
             else if (ws >= 2 && (op.k - op.ksplit_log2) >= 6)
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
+            else if (persist_small_k && (op.k - op.ksplit_log2) <= 5 && blocks > 2ull * 148ull)
+                // K <= 32 per split, more tiles than CTA slots: persistent CTAs prefetch the next tiles
+                GEMM_76_P<<<2 * 148, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
             else
                 GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
         }

@@ -39,6 +39,9 @@ CASES = [
     (18, 16, 9), (17, 17, 10), (20, 12, 6), (21, 18, 9), (13, 13, 1), (12, 12, 0), (22, 8, 8),
     (12, 11, 2), (11, 13, 3), (14, 10, 3), (16, 3, 1), (17, 2, 0),  # small-k GEMM (zero-filled K step) and x4 streaming kernel
     (14, 14, 8), (15, 14, 8), (16, 16, 10), (22, 22, 16),  # 64x64 tiles, 128x64 tiles, split-K with few tiles
+    # short K with more tiles than CTA slots: the persistent kernel (partial K step, one and two K steps per tile,
+    # one tile column, swapped operands)
+    (15, 13, 2), (16, 14, 4), (17, 15, 5), (19, 9, 3), (11, 20, 4), (14, 13, 1),
 ]
 
 
