@@ -1173,7 +1173,11 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             // (UBLKCP: 2.4x SLOWER, request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
             static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 4;
             static const bool persist_small_k = !(getenv("TOB_GEMM_PERSIST") && atoi(getenv("TOB_GEMM_PERSIST")) == 0);
-            if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
+            static const int persist_k = getenv("TOB_GEMM_PERSIST_K") ? atoi(getenv("TOB_GEMM_PERSIST_K")) : 5;  // log2 of the longest K
+            if (persist_small_k && (op.k - op.ksplit_log2) <= persist_k && blocks > 2ull * 148ull)
+                // K <= 32 per split, more tiles than CTA slots: persistent CTAs prefetch the next tiles
+                GEMM_76_P<<<2 * 148, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+            else if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
                 GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else if (ws == 4 && (op.k - op.ksplit_log2) >= 8)
                 GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
@@ -1186,9 +1190,6 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 GEMM_76_WZ<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
             else if (ws >= 2 && (op.k - op.ksplit_log2) >= 6)
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
-            else if (persist_small_k && (op.k - op.ksplit_log2) <= 5 && blocks > 2ull * 148ull)
-                // K <= 32 per split, more tiles than CTA slots: persistent CTAs prefetch the next tiles
-                GEMM_76_P<<<2 * 148, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
             else
                 GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
         }
