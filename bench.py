@@ -8,25 +8,33 @@ instance, planning excluded; % of FP64/HBM roofline for the dominant kernel).
 A *step* = one pass over the workload: every instance of the cubic vertex-cover family
 (n = 50..220 step 10; n=50 is the instance the reference ships, the others are regenerated with the
 same recipe) contracted along its stored line-Flow plan.  The upper end is what
-the reference's CPU path can also time within minutes, so both arms run the IDENTICAL workload; the
-larger members (n = 230..250) are timed separately (`large_instances`) and `--workload sliced250` is
-BASELINE config 4.  Instances with
-n >= 200 use the reference slicer's `minimum_slice=3` plan (8 slices) at EVERY N so the same work is
-compared at 1/2/4/8 GPUs: rank r contracts slices r, r+N, ... ; unsliced instances are independent
-objects and are spread over the ranks (longest first); one NCCL all-reduce combines the count vector.
+the reference's CPU path can also time within minutes, so BOTH ARMS RUN THE IDENTICAL 18 INSTANCES; the
+larger members (n = 230..250) are timed separately (`large_instances`).  Instances with n >= 200 use the
+reference slicer's `minimum_slice=3` plan (8 slices) at EVERY N so the same work is compared at 1/2/4/8
+GPUs: rank r contracts slices r, r+N, ... ; unsliced instances are independent objects and are spread over
+the ranks (longest first, by the compiled programs' cost); one NCCL all-reduce combines the count vector.
 
-  value : inputs resident in HBM (plans compiled, leaves uploaded) when the timed region starts;
-          timed with CUDA events on the stream the kernels run on, one event pair per step, an L2
-          flush between steps, MAX over ranks per step.  Per-GEMM event timing is ON in this arm (it feeds
-          `roofline`): GEMMs of the two slice lanes are then chained, which costs ~3 % on the sliced
-          mid-size instances compared with the default (untimed) path the e2e arm runs.
-  e2e   : the same workload through the reference-facing call `B200API.contract_sliced(plan)` with
-          HOST leaf buffers: flatten + plan compile + arena allocation + pinned H2D of the leaves +
-          kernels + D2H of the count inside the timed region, every step.
-  --impl reference : the reference's CPU path (oracle port: the same numpy.tensordot calls the
-          reference's numpy backend makes) on all host cores, on a bounded sample of the workload.
+  value : inputs resident in HBM (plans compiled, leaves uploaded) when the timed region starts.  All of
+          a rank's instances are issued asynchronously (tob_plan_run_async: every plan on its own streams,
+          ordered behind the timing stream), so the launch-bound stretches of one contraction overlap the
+          GEMMs of another; one CUDA-event pair per step on the timing stream, an L2 flush between steps,
+          MAX over ranks per step.  Per-GEMM event timing is OFF in this arm (it is the default code path).
+  roofline : a separate sequential pass after the timed steps with a CUDA-event pair around every DMMA GEMM
+          (algorithmic flops / summed durations); the FP64 peak is MEASURED IN THIS RUN (cuBLAS DGEMM 8192^3
+          through torch.matmul) next to the round-1 calibration and the raw DMMA pipe peak.
+  e2e   : the same workload through the reference-facing call `B200API.contract_sliced(plan)` with HOST
+          leaf buffers: leaf build (`Tensor.build`) + pinned H2D of the leaves + kernels + D2H of the count
+          inside the timed region, every step; the plan compile is paid once per plan (plan cache keyed
+          by plan identity) in the untimed warm-up pass.
+  extra : BASELINE configs 3, 4 and 5 measured in the same run: `weighted150` (n=150 mcc weights,
+          factor-Flow), `sliced250` (n=250, 8 slices, at this N), `rank_sweep` (N=1).
+  --impl reference : the REAL reference (oracle/_ref: vardigroup/TensorOrder's own
+          `NumpyAPI.contract_sliced` on reference objects rebuilt from the same stored plans) on all host
+          cores, over the same 18 instances.
 """
 import argparse
+import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -39,47 +47,48 @@ sys.path.insert(0, REPO)
 GOLDEN = os.path.join(REPO, "tests", "golden")
 METRIC = "contraction s/instance (plan excluded)"
 UNIT = "s/instance"
-FP64_PEAK_TFLOPS = 35.49  # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01_fp64_calibration.txt);
-# MEASURED_PEAKS.json has no FP64 entry (bf16 + HBM only).  Raw DMMA pipe peak measured 37.1.
+FP64_CUBLAS_CALIBRATION = 35.49  # cuBLAS DGEMM 8192^3 on this pool's B200s, round 1 (profiles/r01_fp64_calibration.txt)
+FP64_DMMA_PIPE = 37.1            # raw DMMA.8x8x4 issue peak measured by tools/fp64_peak.cu (same file)
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return {}
 
 
 def workload_config(args):
-    if args.workload == "sliced250":
-        return {
-            "workload": "cubic_vc n=250 (random 3-regular vertex cover, seed 0), stored line-Flow plan sliced by the "
-                        "reference slicer with minimum_slice=%d (%d slices), unweighted float64 (BASELINE config 4)"
-                        % (args.slice_bits, 2 ** args.slice_bits),
-            "planner": "line-Flow",
-            "l2": "256 MiB write between steps; dominant operands exceed the 126 MB L2",
-            "parallelism": "slices r::N, one all-reduce of the count",
-        }
     return {
         "workload": "cubic_vc family n=%d..%d step 10 (random 3-regular vertex cover, seed 0; n=50 is the shipped "
                     "benchmarks/cubic_vertex_cover/cubic_vc_50_0.cnf), stored line-Flow plans, unweighted float64; "
-                    "n>=200 as the reference slicer's minimum_slice=3 plans (8 slices)" % (args.min_n, args.max_n),
+                    "n>=200 as the reference slicer's minimum_slice=3 plans (8 slices); %d instances, identical in "
+                    "both arms" % (args.min_n, args.max_n, len(range(args.min_n, args.max_n + 1, 10))),
         "planner": "line-Flow",
         "l2": "256 MiB write between steps; dominant operands exceed the 126 MB L2",
         "parallelism": "slices r::N of sliced instances, unsliced instances spread over ranks, one all-reduce of the counts",
     }
 
 
-def load_workload(min_n, max_n, workload="family", slice_bits=3):
+def load_workload(min_n, max_n):
     from tensororder_b200.plan_format import PortablePlan
 
     items = []
-    if workload == "sliced250":
-        pp = PortablePlan.load(os.path.join(GOLDEN, "vc250_lineflow.json.gz"))
-        var = pp.variant("min%d" % slice_bits)
-        return [{"n": 250, "name": var.name, "pp": var, "expected": var.expected.get("count", pp.expected.get("count")),
-                 "cost": pp.expected.get("estimated_flops", 0.0)}]
     for n in range(min_n, max_n + 1, 10):
         pp = PortablePlan.load(os.path.join(GOLDEN, "vc%d_lineflow.json.gz" % n))
         unsliced_expected = pp.expected
         if n >= 200:
             pp = pp.variant("min3")
-        items.append({"n": n, "name": pp.name, "pp": pp, "expected": unsliced_expected.get("count"),
+        items.append({"n": n, "name": pp.name, "pp": pp, "expected": unsliced_expected.get("count", pp.expected.get("count")),
                       "cost": unsliced_expected.get("estimated_flops", 0.0)})
     return items
+
+
+def rel_ok(got, want, tol=1e-9):
+    return want is not None and abs(got - want) <= tol * abs(want)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -158,51 +167,273 @@ def use_all_cores():
         pass
 
 
-def run_cpu_sample(items):
-    """The reference's numpy path (oracle port) over `items`; returns seconds and counts."""
-    from oracle import numpy_oracle
+class CpuArm:
+    """The reference's CPU implementation of the path over the workload's instances.  kind "reference": the
+    real thing (oracle/_ref — `NumpyAPI.contract_sliced`, src/tensor_network/tensor_apis/base_api.py:17-28 +
+    numpy_apis.py:42-55, driving `TensorNetwork.slice_groups` and `identify` on reference objects rebuilt from
+    the stored plans); kind "port": the numpy restatement (oracle/numpy_oracle.py), only when oracle/_ref was
+    never built."""
 
-    use_all_cores()
+    def __init__(self, items):
+        from oracle import reference
 
-    t0 = time.perf_counter()
-    counts = [float(numpy_oracle.contract_sliced(it["pp"].to_json())) for it in items]
-    return time.perf_counter() - t0, counts
+        use_all_cores()
+        self.items = items
+        self.kind = "reference" if reference.available() else "port"
+        if self.kind == "reference":
+            R = reference.import_reference()
+            self.api = R["tensor_network"].ALL_APIS["numpy"]()
+            self.api.add_argument("entry_type", "float64")
+            self.plans = [reference.to_reference_plan(R, it["pp"]) for it in items]
+        else:
+            self.docs = [it["pp"].to_json() for it in items]
+
+    def one_pass(self):
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            counts = [float(self.api.contract_sliced(p)) for p in self.plans]
+        else:
+            from oracle import numpy_oracle
+
+            counts = [float(numpy_oracle.contract_sliced(d)) for d in self.docs]
+        return time.perf_counter() - t0, counts
+
+    def counts_ok(self, counts):
+        return all(it["expected"] is None or rel_ok(c, it["expected"]) for it, c in zip(self.items, counts))
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return  # under torchrun only rank 0 runs the CPU arm
-    use_all_cores()
-
-    items = [it for it in load_workload(args.min_n, args.max_n) if it["n"] <= args.cpu_max_n]
-    n_workload = len(items)
-    # keep the whole K+W run within a few minutes: drop the largest instances if one pass is too slow
-    t_first, _ = run_cpu_sample(items)
-    budget = 240.0
-    while len(items) > 1 and t_first * (args.steps + args.warmup) > budget:
-        items = items[:-1]
-        t_first, _ = run_cpu_sample(items)
-    for _ in range(max(args.warmup - 1, 0)):
-        run_cpu_sample(items)
+    items = load_workload(args.min_n, args.max_n)
+    arm = CpuArm(items)
+    # the instance list is NEVER shortened (both arms run the same instances); if the box is so slow that
+    # W + K passes would take more than ~25 minutes, fewer timed passes are taken and the line says so
+    t_first, counts = arm.one_pass()
+    steps, warmup = args.steps, args.warmup
+    truncated = False
+    budget = 1500.0
+    if t_first * (steps + warmup) > budget:
+        truncated = True
+        warmup = 1
+        steps = max(1, min(steps, int(budget / t_first) - 1))
+    for _ in range(max(warmup - 1, 0)):
+        arm.one_pass()
     total = 0.0
-    counts = None
-    for _ in range(args.steps):
-        dt, counts = run_cpu_sample(items)
+    for _ in range(steps):
+        dt, counts = arm.one_pass()
         total += dt
-    ok = all(it["expected"] is None or abs(c - it["expected"]) <= 1e-9 * abs(it["expected"]) for it, c in zip(items, counts))
-    per_step = total / args.steps
+    per_step = total / steps
     value = per_step / len(items)
     sample = "instances n=%d..%d of the workload (%d of %d), one pass per step" % (
-        items[0]["n"], items[-1]["n"], len(items), n_workload)
+        items[0]["n"], items[-1]["n"], len(items), len(items))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": arm.kind, "sample": sample,
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "counts_ok": bool(ok),
+        "gpu_launches": 0, "counts_ok": bool(arm.counts_ok(counts)), "instances": len(items), "truncated": truncated,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def program_cost_s(desc, slices_per_rank):
+    """Modelled device seconds of one compiled program on one rank: per op max(flops / 33 TF, bytes / 5 TB/s)
+    plus a launch latency; the slice-invariant prologue once, the per-slice list once per slice this rank runs."""
+    def ops_cost(ops):
+        t = 0.0
+        for op in ops:
+            t += max(op.get("flops", 0.0) / 33e12, op.get("bytes", 0.0) / 5e12) + 3e-6
+        return t
+    return ops_cost(desc["invariant_ops"]) + slices_per_rank * ops_cost(desc["slice_ops"])
+
+
+def measure_fp64_peak(torch, dev, n=8192, reps=6):
+    """cuBLAS DGEMM n^3 through torch.matmul, best of `reps` (CUDA events): the FP64 roofline denominator measured in
+    this run (MEASURED_PEAKS.json carries only bf16 and HBM figures)."""
+    a = torch.rand(n, n, dtype=torch.float64, device=dev)
+    b = torch.rand(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    best = None
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None or ms < best else best
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def lib_build_id():
+    from tensororder_b200 import cabi
+
+    h = hashlib.sha256()
+    with open(cabi.LIB_PATH, "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def gemm_traffic():
+    """DRAM bytes of one dominant GEMM launch from an `ncu --set full` capture of THIS build
+    (tools/ncu_gemm_traffic.sh writes profiles/gemm_traffic.json with the library's build id)."""
+    path = os.path.join(REPO, "profiles", "gemm_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    doc = json.load(open(path))
+    return doc.get("dram_bytes_per_launch"), {
+        "source": "profiles/gemm_traffic.json (ncu --set full, one launch of the join it names)",
+        "join": doc.get("join"), "algorithmic_bytes": doc.get("algorithmic_bytes"),
+        "captured_build": doc.get("lib_build_id"), "this_build": lib_build_id(),
+        "same_build": doc.get("lib_build_id") == lib_build_id()}
+
+
+# --------------------------------------------------------------------------------------------------
+def extra_weighted150(torch, dev, local_rank, hbm_gbs, fp64_peak):
+    """BASELINE config 3: n=150 with random literal weights (mcc), factor-Flow tree, float64, one GPU."""
+    from tensororder_b200.api import B200API, CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+    from tensororder_b200.plan_format import PortablePlan
+
+    pp = PortablePlan.load(os.path.join(GOLDEN, "vc150_mcc_factorflow.json.gz"))
+    want = pp.expected["count"]
+    cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), device=local_rank)
+    cp.upload()
+    for _ in range(3):
+        got = cp.run()
+    ms = []
+    for _ in range(10):
+        got = cp.run()
+        ms.append(cp.last_ms)
+    desc = cp.describe()
+    ops = desc["invariant_ops"] + desc["slice_ops"]
+    cp.profile(0)
+    per_op, _ = cp.profile(0)
+    nodes = []
+    for t, op in sorted(zip(per_op, ops), key=lambda x: -x[0])[:4]:
+        if op["kind"] not in (0, 1) or t <= 0:
+            continue
+        tf = op["flops"] / (t * 1e-3) / 1e12
+        gb = op["bytes"] / (t * 1e-3) / 1e9
+        bound = "tensor" if op["flops"] / (fp64_peak * 1e12) > op["bytes"] / (hbm_gbs * 1e9) else "hbm"
+        nodes.append({"m": op["m"], "n": op["n"], "k": op["k"], "kernel": "gemm" if op["kind"] == 1 else "generic",
+                      "ksplit_log2": op["ksplit_log2"], "ms": t, "tflops": tf, "gbs": gb, "bound": bound,
+                      "frac": tf / fp64_peak if bound == "tensor" else gb / hbm_gbs})
+    cp.close()
+    api = B200API()
+    api.add_argument("entry_type", "float64")
+    api.add_argument("device", local_rank)
+    api.add_argument("distributed", False)
+    plan = pp.as_execution_plan()
+    api.contract_sliced(plan)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        e2e_got = float(api.contract_sliced(plan))
+    e2e_s = (time.perf_counter() - t0) / reps
+    ms.sort()
+    return {"config": "BASELINE config 3: cubic_vc n=150 + mcc literal weights U(0.5,1.5), factor-Flow, float64, 1 GPU",
+            "device_seconds": ms[len(ms) // 2] / 1e3, "e2e_seconds": e2e_s, "count": got, "reference_count": want,
+            "rel_err": abs(got - want) / abs(want), "count_ok": bool(rel_ok(got, want) and rel_ok(e2e_got, want)),
+            "tolerance": 1e-9, "dominant_nodes": nodes}
+
+
+def extra_sliced250(torch, dist, dev, local_rank, rank, world, passes=2):
+    """BASELINE config 4: n=250 sliced by the reference slicer (minimum_slice=3 -> 8 slices), slices r::N,
+    one all-reduce of the count; the SAME plan at every N."""
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+    from tensororder_b200.plan_format import PortablePlan
+
+    pp = PortablePlan.load(os.path.join(GOLDEN, "vc250_lineflow.json.gz")).variant("min3")
+    want = pp.expected.get("count")
+    cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), device=local_rank)
+    cp.upload()
+    stream = torch.cuda.Stream(device=dev)
+    cp.set_stream(stream.cuda_stream)
+    secs, got = [], None
+    for i in range(1 + passes):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            part = cp.run(first=rank, stride=world)
+            vec = torch.tensor([part], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(vec)
+            e1.record(stream)
+        stream.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i >= 1:
+            secs.append(float(t.item()) / 1e3)
+        got = float(vec.item())
+    out = {"config": "BASELINE config 4: cubic_vc n=250, stored line-Flow plan, reference slicer minimum_slice=3 "
+                     "(8 slices), slices r::N + one NCCL all-reduce of the count",
+           "n_gpus": world, "slices": cp.num_slices, "seconds": min(secs), "seconds_all": secs, "count": got,
+           "reference_count": want, "count_ok": bool(rel_ok(got, want)), "peak_gb_per_gpu": cp.peak_bytes / 1e9,
+           "launches_per_pass_rank0": cp.last_launches}
+    cp.close()
+    return out
+
+
+SWEEP_POINTS = [(28, 8), (28, 12), (28, 16), (30, 8), (30, 16), (32, 2), (32, 4), (32, 8), (32, 16), (34, 2), (34, 4), (34, 12)]
+
+
+def extra_rank_sweep(torch, dev, hbm_gbs, fp64_peak):
+    """BASELINE config 5 digest: single pairwise contractions, T = fL + fR + k total indices, k contracted,
+    GEMM-ready operands (`tob_tensordot_device`); the full sweep is tools/rank_sweep.py."""
+    import numpy as np
+
+    from tensororder_b200 import cabi
+
+    P32 = ctypes.POINTER(ctypes.c_int32)
+    rows = []
+    for T, k in SWEEP_POINTS:
+        fL = (T - k + 1) // 2
+        fR = T - k - fL
+        ra, rb, rc = fL + k, fR + k, fL + fR
+        a = torch.rand(1 << ra, dtype=torch.float64, device=dev)
+        b = torch.rand(1 << rb, dtype=torch.float64, device=dev)
+        c = torch.empty(1 << rc, dtype=torch.float64, device=dev)
+        ws_bytes = 8 * min(1 << (rc + 6), 1 << 28) + 4096
+        ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+        aa = np.arange(ra - k, ra, dtype=np.int32)
+        ab = np.arange(rb - k, rb, dtype=np.int32)
+        best = None
+        for rep in range(4):
+            ms = (ctypes.c_float * 3)()
+            torch.cuda.synchronize(dev)
+            rc_ = cabi.lib.tob_tensordot_device(a.data_ptr(), ra, b.data_ptr(), rb, aa.ctypes.data_as(P32),
+                                                ab.ctypes.data_as(P32), k, c.data_ptr(), ws.data_ptr(), ws_bytes, 0, None, ms)
+            if rc_ != 0:
+                raise RuntimeError(cabi.last_error())
+            if rep and (best is None or ms[1] < best):
+                best = ms[1]
+        flops = 2.0 * 2.0 ** T
+        byts = 8.0 * (2.0 ** ra + 2.0 ** rb + 2.0 ** rc)
+        tf = flops / (best * 1e-3) / 1e12
+        gb = byts / (best * 1e-3) / 1e9
+        bound = "tensor" if flops / (fp64_peak * 1e12) > byts / (hbm_gbs * 1e9) else "hbm"
+        rows.append({"T": T, "k": k, "ms": best, "tflops": tf, "gbs": gb, "bound": bound,
+                     "frac": tf / fp64_peak if bound == "tensor" else gb / hbm_gbs})
+        del a, b, c, ws
+        torch.cuda.empty_cache()
+    return {"config": "BASELINE config 5 digest: single contractions, T total / k contracted indices, GEMM-ready operands",
+            "points": rows}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -211,7 +442,7 @@ def b200_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from tensororder_b200.api import B200API, CompiledPlan
+    from tensororder_b200.api import PLAN_CACHE, B200API, CompiledPlan
     from tensororder_b200.flatten import flatten_plan
 
     torch.cuda.set_device(local_rank)
@@ -231,22 +462,32 @@ def b200_arm(args, rank, world, local_rank):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    items = load_workload(args.min_n, args.max_n, args.workload, args.slice_bits)
+    peaks = measured_peaks()
+    hbm_gbs = float(peaks.get("hbm_gbs", 6552.6))
+    items = load_workload(args.min_n, args.max_n)
     n_inst = len(items)
 
-    # ---- partition: sliced instances are shared by all ranks, unsliced ones go to one rank (LPT) ----
+    # ---- partition: sliced instances are shared by all ranks, unsliced ones go to one rank (longest first), by the
+    # modelled cost of the COMPILED programs: a shared instance costs every rank its replicated slice-invariant
+    # prologue plus its share of the slices ----
     load = [0.0] * world
-    for it in sorted(items, key=lambda x: -x["cost"]):
-        nsl = 2 ** len([g for g in it["pp"].groups_to_slice if len(g)])
-        if nsl >= world and world > 1 and nsl > 1:
+    for it in items:
+        cp = CompiledPlan(flatten_plan(it["pp"].as_execution_plan()), device=local_rank)  # host only
+        it["nsl"] = cp.num_slices
+        it["shared"] = world > 1 and it["nsl"] > 1 and it["nsl"] >= world
+        it["model_s"] = program_cost_s(cp.describe(), (it["nsl"] + world - 1) // world if it["shared"] else it["nsl"])
+        cp.close()
+    for it in items:
+        if it["shared"]:
             it["owner"] = None
             for r in range(world):
-                load[r] += it["cost"] / world
-        else:
-            r = min(range(world), key=lambda q: load[q])
-            it["owner"] = r
-            load[r] += it["cost"]
+                load[r] += it["model_s"]
+    for it in sorted([x for x in items if not x["shared"]], key=lambda x: -x["model_s"]):
+        r = min(range(world), key=lambda q: load[q])
+        it["owner"] = r
+        load[r] += it["model_s"]
     mine = [it for it in items if it["owner"] in (None, rank)]
+    mine.sort(key=lambda x: -x["model_s"])  # issue order: the long GEMM-heavy contractions first
 
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -265,13 +506,12 @@ def b200_arm(args, rank, world, local_rank):
     for it in mine:
         cp = CompiledPlan(flatten_plan(it["pp"].as_execution_plan()), device=local_rank)
         cp.upload()
-        cp.set_stream(stream.cuda_stream)
-        cp.set_gemm_timing(True)  # CUDA-event pair around every DMMA GEMM of the timed steps (roofline)
+        if args.sequential:
+            cp.set_stream(stream.cuda_stream)
         it["cp"] = cp
+    index = {it["name"]: j for j, it in enumerate(items)}
     counts = torch.zeros(n_inst, dtype=torch.float64, device=dev)
     step_ms, launches = [], 0
-    gemm_ms = gemm_flops = 0.0
-    gemm_launches = 0
     sampler = ClockSampler(local_rank)
     for step in range(args.warmup + args.steps):
         timed = step >= args.warmup
@@ -287,25 +527,26 @@ def b200_arm(args, rank, world, local_rank):
             torch.cuda.nvtx.range_push("timed_step")  # ncu --nvtx --nvtx-include "timed_step/" selects these launches
         with torch.cuda.stream(stream):
             e0.record(stream)
-            for j, it in enumerate(items):
-                if it["owner"] is None:
-                    host[j] = it["cp"].run(first=rank, stride=world)
-                elif it["owner"] == rank:
-                    host[j] = it["cp"].run()
-                else:
-                    continue
-                if timed:
-                    launches += it["cp"].last_launches
-                    g = it["cp"].last_gemm
-                    gemm_ms += g[0]
-                    gemm_flops += g[1]
-                    gemm_launches += g[2]
+            if args.sequential:
+                for it in mine:
+                    host[index[it["name"]]] = it["cp"].run(first=rank, stride=world) if it["owner"] is None else it["cp"].run()
+            else:
+                for it in mine:  # all of this rank's contractions in flight at once, each on its own streams
+                    if it["owner"] is None:
+                        it["cp"].run_async(first=rank, stride=world, after_stream=stream.cuda_stream)
+                    else:
+                        it["cp"].run_async(after_stream=stream.cuda_stream)
+                for it in mine:
+                    it["cp"].join(stream.cuda_stream)
+                for it in mine:
+                    host[index[it["name"]]] = it["cp"].wait()
             counts.copy_(torch.from_numpy(host))
             reduce_counts(counts)
             e1.record(stream)
         stream.synchronize()
         if timed:
             torch.cuda.nvtx.range_pop()
+            launches += sum(it["cp"].last_launches for it in mine)
         barrier()
         if timed:
             step_ms.append(e0.elapsed_time(e1))
@@ -317,6 +558,21 @@ def b200_arm(args, rank, world, local_rank):
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
     ms_per_step = float(t.sum().item()) / args.steps
     value_counts = counts.cpu().numpy().copy()
+
+    # ---- roofline pass: the same plans, sequentially, a CUDA-event pair around every DMMA GEMM ----
+    gemm_ms = gemm_flops = seq_ms = 0.0
+    gemm_launches = 0
+    for it in mine:
+        it["cp"].set_gemm_timing(True)
+        if it["owner"] is None:
+            it["cp"].run(first=rank, stride=world)
+        else:
+            it["cp"].run()
+        g = it["cp"].last_gemm
+        gemm_ms += g[0]
+        gemm_flops += g[1]
+        gemm_launches += g[2]
+        seq_ms += it["cp"].last_ms
     for it in mine:
         it["cp"].close()
         del it["cp"]
@@ -329,24 +585,24 @@ def b200_arm(args, rank, world, local_rank):
     e2e_counts = None
     e2e_parts = {"flatten_compile_s": 0.0, "upload_s": 0.0, "run_s": 0.0, "device_ms": 0.0}
     e2e_step_s = []
-    for step in range(1 + e2e_steps):  # one warm-up pass
+    cache_hits = 0
+    for step in range(1 + e2e_steps):  # one warm-up pass (pays the plan compiles: cached by plan identity afterwards)
         barrier()
         t0 = time.perf_counter()
         host = np.zeros(n_inst)
         h2d = d2h = 0
-        for j, it in enumerate(items):
-            if it["owner"] not in (None, rank):
-                continue
+        for it in mine:
             api = B200API()
             api.add_argument("entry_type", "float64")
             api.add_argument("device", local_rank)
             api.add_argument("distributed", it["owner"] is None)
             got = float(api.contract_sliced(plans[it["name"]]))
             # sliced instances come back already all-reduced (identical on every rank): count them once
-            host[j] = got / world if it["owner"] is None else got
+            host[index[it["name"]]] = got / world if it["owner"] is None else got
             h2d += api.last_stats["h2d_bytes"]
             d2h += api.last_stats["d2h_bytes"]
             if step >= 1:
+                cache_hits += int(api.last_stats["plan_cache_hit"])
                 for key in e2e_parts:
                     e2e_parts[key] += api.last_stats[key]
         vec = torch.from_numpy(host).to(dev)
@@ -363,13 +619,14 @@ def b200_arm(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
     e2e_value = e2e_total / e2e_steps / n_inst
+    PLAN_CACHE.clear()
 
-    # =============================== checks, CPU baseline, report ================================
+    # =============================== checks, extras, CPU baseline, report ========================
     def counts_ok(vec):
         ok = True
         for it, c in zip(items, vec):
             if it["expected"] is not None:
-                ok &= abs(c - it["expected"]) <= 1e-9 * abs(it["expected"])
+                ok &= rel_ok(c, it["expected"])
             else:
                 ok &= bool(np.isfinite(c) and c > 0)
         return bool(ok)
@@ -377,39 +634,49 @@ def b200_arm(args, rank, world, local_rank):
     ok = counts_ok(value_counts) and counts_ok(e2e_counts) and bool(
         np.allclose(value_counts, e2e_counts, rtol=1e-12, atol=0))
 
+    extra = {}
+    if not args.no_extra:
+        extra["sliced250"] = extra_sliced250(torch, dist, dev, local_rank, rank, world)
     if rank == 0:
+        fp64_live = measure_fp64_peak(torch, dev)
         line = {
             "metric": METRIC, "value": ms_per_step / 1e3 / n_inst, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
-                    "step_seconds": e2e_step_s,
+                    "step_seconds": e2e_step_s, "plan_cache_hits_rank0": cache_hits,
                     "rank0_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(lt.item()), "clocks": clocks, "counts_ok": ok, "instances": n_inst,
+            "issue": "sequential" if args.sequential else "async: all of a rank's instances in flight",
+            "rank0": {"instances": [it["n"] for it in mine], "sequential_device_ms": seq_ms,
+                      "modelled_load_s": load},
         }
         if gemm_launches > 0:
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-            traffic = None
-            tpath = os.path.join(REPO, "profiles", "gemm_traffic.json")
-            if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic, traffic_note = gemm_traffic()
             line["roofline"] = {
-                "bound": "tensor", "kernel": "k_gemm_dmma (DMMA.8x8x4 FP64)", "achieved": achieved,
-                "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                "bound": "tensor", "kernel": "k_gemm_dmma* (DMMA.8x8x4 FP64)", "achieved": achieved,
+                "peak": fp64_live, "unit": "TFLOP/s", "frac": achieved / fp64_live, "traffic": traffic,
                 "launches": int(gemm_launches), "avg_launch_ms": gemm_ms / gemm_launches,
                 "flops_per_launch": gemm_flops / gemm_launches,
-                "peak_source": "measured cuBLAS DGEMM 8192^3 on this pool (profiles/r01_fp64_calibration.txt); "
+                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul, best of 6, CUDA events) measured in THIS run; "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "share_of_step": gemm_ms / (ms_per_step * args.steps),
+                "peak_round1_calibration": FP64_CUBLAS_CALIBRATION, "frac_of_round1_calibration": achieved / FP64_CUBLAS_CALIBRATION,
+                "dmma_pipe_peak": FP64_DMMA_PIPE, "frac_of_dmma_pipe": achieved / FP64_DMMA_PIPE,
+                "measured": "separate sequential pass over rank 0's instances after the timed steps, one CUDA-event pair per GEMM launch",
+                "gemm_ms_rank0": gemm_ms, "share_of_step": gemm_ms / ms_per_step, "traffic_note": traffic_note,
             }
-        if world == 1 and args.workload == "family" and not args.no_large:
+        if world == 1 and not args.no_large:
             # beyond what the CPU arm can time: the largest family members, one pass each (device time)
             from tensororder_b200.plan_format import PortablePlan
 
             large = []
             for n in (230, 240, 250):
                 pp = PortablePlan.load(os.path.join(GOLDEN, "vc%d_lineflow.json.gz" % n))
+                want = pp.expected.get("count")
+                if want is None:  # the reference replayed the 8-slice plan of this instance (tests/golden/ref_replay.py)
+                    want = pp.variant("min3").expected.get("count")
                 cp = CompiledPlan(flatten_plan(pp.as_execution_plan()), device=local_rank)
                 cp.upload()
                 cp.set_gemm_timing(True)
@@ -419,31 +686,38 @@ def b200_arm(args, rank, world, local_rank):
                 large.append({"n": n, "seconds": cp.last_ms / 1e3, "count": c, "peak_gb": cp.peak_bytes / 1e9,
                               "gemm_tflops": (g[1] / (g[0] * 1e-3) / 1e12) if g[0] > 0 else None,
                               "gemm_share": g[0] / cp.last_ms if cp.last_ms > 0 else None,
-                              "reference_count": pp.expected.get("count")})
+                              "reference_count": want, "count_ok": bool(rel_ok(c, want))})
                 cp.close()
             line["large_instances"] = large
-        if world == 1 and args.workload == "family" and not args.no_cpu_baseline:
-            sample_items = [it for it in items if it["n"] <= args.cpu_max_n]
+        if not args.no_extra:
+            extra["weighted150"] = extra_weighted150(torch, dev, local_rank, hbm_gbs, fp64_live)
+            if world == 1:
+                extra["rank_sweep"] = extra_rank_sweep(torch, dev, hbm_gbs, fp64_live)
+        line["extra"] = extra
+        if world == 1 and not args.no_cpu_baseline:
             # our own arm on exactly the same sample (apples to apples next to the CPU number); before the CPU
             # pass, whose BLAS threads keep spinning for a while afterwards
             api_s = 0.0
-            for it in sample_items:
+            fresh = {it["name"]: it["pp"].as_execution_plan() for it in items}
+            for it in items:
                 api = B200API()
                 api.add_argument("entry_type", "float64")
                 t0 = time.perf_counter()
-                api.contract_sliced(plans[it["name"]])
+                api.contract_sliced(fresh[it["name"]])
                 api_s += time.perf_counter() - t0
-            cpu_s, cpu_counts = run_cpu_sample(sample_items)
-            cpu_ok = all(it["expected"] is None or abs(c - it["expected"]) <= 1e-9 * abs(it["expected"])
-                         for it, c in zip(sample_items, cpu_counts))
+            PLAN_CACHE.clear()
+            arm = CpuArm(items)
+            cpu_s, cpu_counts = arm.one_pass()
             line["cpu_baseline"] = {
-                "value": cpu_s / len(sample_items), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                "value": cpu_s / len(items), "unit": UNIT, "cores": cpu_threads(), "kind": arm.kind,
                 "sample": "instances n=%d..%d of the workload (%d of %d), one pass" % (
-                    sample_items[0]["n"], sample_items[-1]["n"], len(sample_items), n_inst),
-                "counts_ok": bool(cpu_ok), "b200_e2e_same_sample": api_s / len(sample_items),
+                    items[0]["n"], items[-1]["n"], len(items), n_inst),
+                "counts_ok": bool(arm.counts_ok(cpu_counts)), "host_cpus": os.cpu_count(),
+                "b200_e2e_same_sample_cold": api_s / len(items),
             }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -455,10 +729,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--min-n", type=int, default=50)
     ap.add_argument("--max-n", type=int, default=220)
-    ap.add_argument("--cpu-max-n", type=int, default=220, help="largest instance in the bounded CPU sample")
-    ap.add_argument("--workload", default="family", choices=["family", "sliced250"])
-    ap.add_argument("--slice-bits", type=int, default=3, choices=[3, 6])
     ap.add_argument("--no-large", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3, 4, 5 (extra blocks)")
+    ap.add_argument("--sequential", action="store_true", help="value arm: one instance after the other on one stream")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

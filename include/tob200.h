@@ -99,6 +99,19 @@ int64_t tob_plan_describe(const tob_plan* plan, char* buf, int64_t cap);
  * (src/tensor_network/tensor_network_constructions.py:69-99,144-152). */
 int tob_plan_upload(tob_plan* plan, const double* leaf_data, int64_t n_doubles);
 
+/* Plan cache support (SURVEY.md §8b "Ownership": the backend owns all device memory and must release it
+ * per call or cache it keyed by plan identity).  tob_plan_update_leaves re-reads the caller's leaf values
+ * into an already uploaded plan (one pinned H2D copy of the leaf region; arena, tables and captured graphs
+ * are kept), or behaves like tob_plan_upload when the plan holds no device memory.  tob_plan_release
+ * returns the plan's device and pinned blocks to the process-wide pool and keeps the compiled program, so a
+ * later tob_plan_upload costs no recompilation. */
+int tob_plan_update_leaves(tob_plan* plan, const double* leaf_data, int64_t n_doubles);
+int tob_plan_release(tob_plan* plan);
+
+/* Frees every cached (idle) device and pinned block of the process-wide pool; device < 0 = all devices.
+ * For hosts that share the GPU with other allocators (e.g. torch). */
+int tob_pool_trim(int32_t device);
+
 /* Contracts slices first, first+stride, ... (count of them) and writes the float64 sum of their
  * rank-0 results to *result (host).  Replaces the loop of BaseTensorAPI.contract_sliced
  * (base_api.py:21-28); count = min(num_slice_limit, 2^s) with first=0, stride=1 reproduces it;
@@ -112,6 +125,17 @@ int tob_plan_run(tob_plan* plan, uint64_t first, uint64_t count, uint64_t stride
 #define TOB_RUN_SKIP_INVARIANT 1
 int tob_plan_run_ex(tob_plan* plan, uint64_t first, uint64_t count, uint64_t stride, double initial,
                     int32_t flags, double* result);
+
+/* Asynchronous form, for hosts that keep several independent plans in flight on one GPU (the launch-bound
+ * stretches of one contraction then overlap the GEMMs of another): tob_plan_run_async issues the run on the
+ * plan's stream(s) and returns; when after_stream (a cudaStream_t) is not NULL the run starts behind the work
+ * already enqueued on it.  tob_plan_join makes `stream` wait (on the device) for the run's last kernel;
+ * tob_plan_wait blocks the host until the run is complete and returns its result like tob_plan_run_ex.
+ * One run in flight per plan; at most 4096 slices per asynchronous call. */
+int tob_plan_run_async(tob_plan* plan, uint64_t first, uint64_t count, uint64_t stride, double initial,
+                       int32_t flags, void* after_stream);
+int tob_plan_join(tob_plan* plan, void* stream);
+int tob_plan_wait(tob_plan* plan, double* result);
 
 /* Device time (CUDA events on the plan's stream) of the last tob_plan_run, in milliseconds. */
 double tob_plan_last_ms(const tob_plan* plan);
@@ -171,6 +195,19 @@ int tob_tensordot_host(const double* a, int32_t rank_a, const double* b, int32_t
 /* Index permutation of a rank-r binary tensor, numpy.transpose semantics: out = in.transpose(perm).
  * DEVICE pointers.  (Stand-alone kernel of north_star item (1); 16 B moved per element.) */
 int tob_permute_device(const double* in, double* out, int32_t rank, const int32_t* perm, void* stream, float* ms);
+
+/* Per-join dispatch parameters (generic <-> GEMM crossover, kernel classes, the split-K time model).  The
+ * defaults are the measured table tensororder_b200/csrc/tob_dispatch_table.h, generated by
+ * tools/fit_dispatch.py; these two calls read / override single values (experiments and the fit itself).
+ * They affect plans created afterwards.  Keys: see `kTuneFields` in csrc/tob_compile.cpp. */
+int tob_tuning_set(const char* key, double value);
+int tob_tuning_get(const char* key, double* value);
+/* The split-K time model the plan compiler minimises (microseconds) for a DMMA GEMM join with K split 2^c ways. */
+double tob_gemm_time_model_us(int32_t m, int32_t n, int32_t k, int32_t tm_log2, int32_t tn_log2, int32_t c);
+
+/* Creates the CUDA context on `device` and primes the block / stream pools, so the first contraction does not pay
+ * for it (TOB_E_NODEVICE without a GPU).  Optional: every entry point initialises the device on demand. */
+int tob_warm(int32_t device);
 
 int tob_device_count(void);
 const char* tob_version(void);

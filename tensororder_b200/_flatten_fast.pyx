@@ -161,3 +161,30 @@ def flatten_tree(plan, dict group_of):
         raise ValueError("contraction tree is not a single rooted tree")
     return (_as_array(node_left), _as_array(node_right), _as_array(node_leaf), _as_array(leaf_rank),
             _as_array64(leaf_off), _as_array(axis_start), _as_array(axis_edge), arena.data(), leaf_tensor_index)
+
+
+def rebuild_leaves(network, list leaf_tensor_index, cnp.ndarray leaf_rank, cnp.ndarray leaf_off, Py_ssize_t total):
+    """Plan-cache hits: the leaf values re-read through `Tensor.build()` in the order `flatten_tree` stored
+    them; None when they no longer fit the cached structure (see flatten.rebuild_leaf_data)."""
+    cdef LeafArena arena = LeafArena(max(total, 16))
+    cdef object factory = arena.factory
+    cdef set seen = set()
+    cdef Py_ssize_t j, size
+    cdef object t, built
+    cdef int32_t* rk = <int32_t*> cnp.PyArray_DATA(leaf_rank)
+    cdef int64_t* lo = <int64_t*> cnp.PyArray_DATA(leaf_off)
+    for j in range(len(leaf_tensor_index)):
+        t = leaf_tensor_index[j]
+        if t in seen:
+            continue
+        seen.add(t)
+        size = (<Py_ssize_t> 1) << rk[j]
+        if arena.used != lo[j]:
+            return None
+        built = network[t].build(factory)
+        if getattr(built, "size", size) != size:
+            return None
+        arena.commit(built, size)
+    if arena.used != total:
+        return None
+    return arena.data()

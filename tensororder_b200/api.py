@@ -11,14 +11,16 @@ r, r+W, r+2W, ... and the partial counts are combined with one all-reduce (NCCL 
 from __future__ import annotations
 
 import ctypes
+import dataclasses
 import time
+from collections import OrderedDict
 from ctypes import byref, c_double, c_float, c_int32, c_void_p
 from typing import Optional
 
 import numpy as np
 
 from . import cabi
-from .flatten import FlatPlan, flatten_plan
+from .flatten import FlatPlan, flatten_plan, rebuild_leaf_data
 
 
 class OutOfMemoryError(Exception):
@@ -71,6 +73,7 @@ class CompiledPlan:
                  slice_lanes: int = 0, dag_branches: int = 0):
         self.flat = flat
         self._handle = c_void_p()
+        self.interruptible_stats = {"device_ms": 0.0, "launches": 0, "gemm": (0.0, 0.0, 0)}
         desc = cabi.tob_plan_desc()
         desc.n_nodes = flat.n_nodes
         desc.node_left = _ptr(flat.node_left, c_int32)
@@ -129,6 +132,23 @@ class CompiledPlan:
             raise RuntimeError("tob_plan_upload: " + cabi.last_error())
         self.uploaded = True
 
+    def update_leaves(self, leaf_data: Optional[np.ndarray] = None) -> None:
+        """Re-reads the leaf values into an uploaded plan (arena, tables and captured graphs are kept);
+        a full `upload` when the plan holds no device memory."""
+        if leaf_data is not None:
+            self.flat = dataclasses.replace(self.flat, leaf_data=np.ascontiguousarray(leaf_data, dtype=np.float64))
+        rc = cabi.lib.tob_plan_update_leaves(self._handle, _ptr(self.flat.leaf_data, c_double), int(self.flat.leaf_data.shape[0]))
+        if rc == cabi.TOB_E_OOM:
+            raise _oom_class()(cabi.last_error())
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_update_leaves: " + cabi.last_error())
+        self.uploaded = True
+
+    def release_device(self) -> None:
+        """Gives the device arena back (to the library's block pool) and keeps the compiled program."""
+        cabi.lib.tob_plan_release(self._handle)
+        self.uploaded = False
+
     def run(self, first: int = 0, count: Optional[int] = None, stride: int = 1, initial: float = 0.0,
             skip_invariant: bool = False) -> float:
         if count is None:
@@ -140,6 +160,28 @@ class CompiledPlan:
             raise _oom_class()(cabi.last_error())
         if rc != cabi.TOB_OK:
             raise RuntimeError("tob_plan_run: " + cabi.last_error())
+        return out.value
+
+    def run_async(self, first: int = 0, count: Optional[int] = None, stride: int = 1, after_stream: int = 0) -> None:
+        """Issues the run and returns (several plans can be in flight on one GPU); `wait` collects the result.
+        after_stream: a cudaStream_t handle the run is ordered behind."""
+        if count is None:
+            count = (self.num_slices - first + stride - 1) // stride
+        rc = cabi.lib.tob_plan_run_async(self._handle, first, count, stride, 0.0, 0, c_void_p(after_stream or None))
+        if rc == cabi.TOB_E_OOM:
+            raise _oom_class()(cabi.last_error())
+        if rc != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_run_async: " + cabi.last_error())
+
+    def join(self, stream: int) -> None:
+        """Makes `stream` (cudaStream_t handle) wait on the device for the run in flight."""
+        if cabi.lib.tob_plan_join(self._handle, c_void_p(stream or None)) != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_join: " + cabi.last_error())
+
+    def wait(self) -> float:
+        out = c_double(0.0)
+        if cabi.lib.tob_plan_wait(self._handle, byref(out)) != cabi.TOB_OK:
+            raise RuntimeError("tob_plan_wait: " + cabi.last_error())
         return out.value
 
     def run_interruptible(self, first: int = 0, count: Optional[int] = None, stride: int = 1, target_s: float = 0.25):
@@ -220,8 +262,98 @@ class CompiledPlan:
             pass
 
 
+class PlanCache:
+    """Compiled plans keyed by plan identity (SURVEY.md §8b "Ownership": the backend owns all device memory
+    and must release it per call or cache it keyed by plan identity).
+
+    Key: the identity of `plan.tree` and `plan.network` (both held, so the ids stay valid), the slice
+    groups' contents and the compile options.  `execution.run`'s OOM retry (src/execution.py:140-142)
+    changes `groups_to_slice` and `contract_small` (sliced_execution_plan.py:29-56) replaces `plan.tree`,
+    so both miss.  A hit skips the tree walk and the plan compile; the LEAF VALUES are re-read through
+    `Tensor.build()` and copied host -> device on every call.  Small plans (arena <= 256 MiB, 1 GiB in
+    total) stay resident on the device with their captured CUDA graphs; larger ones give their arena back
+    after each call and keep only the compiled program."""
+
+    MAX_ENTRIES = 64
+    RESIDENT_PLAN_BYTES = 256 << 20
+    RESIDENT_TOTAL_BYTES = 1 << 30
+
+    def __init__(self):
+        self.entries = OrderedDict()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def key(plan, options):
+        groups = tuple(tuple(sorted(int(e) for e in g)) for g in plan.groups_to_slice)
+        return (id(plan.tree), id(plan.network), groups, options)
+
+    def lookup(self, plan, options):
+        k = self.key(plan, options)
+        e = self.entries.get(k)
+        if e is not None and e["tree"] is plan.tree and e["network"] is plan.network:
+            self.entries.move_to_end(k)
+            self.hits += 1
+            return e
+        self.misses += 1
+        return None
+
+    def store(self, plan, options, compiled):
+        k = self.key(plan, options)
+        old = self.entries.pop(k, None)
+        if old is not None and old["compiled"] is not compiled:
+            old["compiled"].close()
+        self.entries[k] = {"tree": plan.tree, "network": plan.network, "compiled": compiled}
+        while len(self.entries) > self.MAX_ENTRIES:
+            _, e = self.entries.popitem(last=False)
+            e["compiled"].close()
+
+    def drop(self, plan, options):
+        e = self.entries.pop(self.key(plan, options), None)
+        if e is not None:
+            e["compiled"].close()
+
+    def after_call(self, compiled):
+        """Residency policy: big arenas go back to the pool at once, small ones stay (LRU within the budget)."""
+        if not compiled.uploaded:
+            return
+        if compiled.peak_bytes > self.RESIDENT_PLAN_BYTES:
+            compiled.release_device()
+            return
+        total = 0
+        for e in reversed(self.entries.values()):  # most recently used first
+            c = e["compiled"]
+            if not c.uploaded:
+                continue
+            total += c.peak_bytes
+            if total > self.RESIDENT_TOTAL_BYTES and c is not compiled:
+                c.release_device()
+
+    def clear(self):
+        for e in self.entries.values():
+            e["compiled"].close()
+        self.entries.clear()
+
+
+PLAN_CACHE = PlanCache()
+
+
 class B200API:
-    """Drop-in for `tensor_network.ALL_APIS[...]` entries (src/tensor_network/__init__.py:12-16)."""
+    """Drop-in for `tensor_network.ALL_APIS[...]` entries (src/tensor_network/__init__.py:12-16).
+
+    Entry types (the table of `NumpyAPI.add_argument`, numpy_apis.py:15-22):
+      float64          the DMMA path; counts bit-exact while representable, 1e-9 relative otherwise.
+      bigint           exact Python int: residues modulo ~23-bit primes on the same kernels + CRT.
+      int / uint       numpy's int64 / uint64 arithmetic wraps modulo 2^64, which is a ring homomorphism of
+                       the integers: the exact count is computed as for bigint and reduced modulo 2^64
+                       (two's complement for int) — bit-identical to the reference's wrapped result.  Leaf
+                       values are truncated toward zero exactly as `numpy.full(shape, w, dtype=int64)` does.
+      float32/float16  leaves are rounded to the entry type (as the reference's `create_tensor` does), the
+                       contraction runs in float64 on the DMMA path and the count is rounded back to the
+                       entry type: at least as accurate as numpy's float32 GEMMs (tolerance vs the reference
+                       5e-6 relative for float32, 5e-3 for float16, while the reference stays finite);
+                       tensors still occupy 8 bytes per entry on the device, and `get_entry_size` says so."""
+
+    ENTRY_TYPES = ("float64", "float32", "float16", "uint", "int", "bigint")
 
     def __init__(self):
         self._entry_type = "float64"
@@ -233,16 +365,20 @@ class B200API:
         self._lanes = 0
         self._branches = 0
         self._distributed = True
+        self._mem_limit_bytes = 0
+        self._plan_cache = True
         self.last_stats = {}
 
     # ---- configuration (tensororder.py:205-217, execution.py:82-85) ----
     def add_argument(self, key, value):
         if key == "entry_type":
-            # float64: the DMMA path.  bigint: the reference's exact mode (numpy object arrays of Python ints,
-            # numpy_apis.py:21) done as residues modulo ~23-bit primes on the same kernels + CRT on the host.
-            if value not in ("float64", "bigint"):
-                raise ValueError("Unknown b200 type %s (float64 and bigint are implemented)" % value)
+            if value not in self.ENTRY_TYPES:
+                raise ValueError("Unknown b200 type %s" % value)  # numpy_apis.py:26-27
             self._entry_type = value
+            # both CLIs make this call right after constructing the backend and before their stopwatch starts
+            # (tensororder.py:205-228, execution.py:82-92): the place to create the CUDA context, as the TensorFlow
+            # backend initialises its device at import.  No device: nothing happens here, contract_sliced fails loudly.
+            cabi.lib.tob_warm(self._resolve_device())
         elif key == "thread_limit":
             pass  # BLAS thread cap of the numpy backend; no host threads are used here
         elif key == "device":
@@ -261,12 +397,16 @@ class B200API:
             self._microtree = bool(value)
         elif key == "distributed":
             self._distributed = bool(value)
+        elif key == "mem_limit_bytes":
+            self._mem_limit_bytes = int(value)  # plans needing more raise OutOfMemoryError (=> slice once more)
+        elif key == "plan_cache":
+            self._plan_cache = bool(value)
         else:
             # same message and exception type as BaseTensorAPI.add_argument (base_api.py:9-12)
             raise ValueError("Invalid argument " + str(key) + " for selected tensor_library")
 
     def get_entry_size(self):
-        return 8  # numpy.dtype(float64).itemsize, numpy_apis.py:64-65
+        return 8  # bytes per entry on the device for every entry type (numpy_apis.py:64-65 for float64)
 
     def warm(self):
         self._resolve_device()
@@ -274,93 +414,174 @@ class B200API:
             raise RuntimeError("b200 tensor library: no CUDA device")
 
     # ---- leaf construction: host arrays, like every reference backend (numpy_apis.py:36-40) ----
+    _HOST_DTYPES = {"float64": np.float64, "float32": np.float32, "float16": np.float16, "uint": np.uint64,
+                    "int": np.int64, "bigint": object}
+
     def create_tensor(self, shape, default_value=None):
+        dtype = self._HOST_DTYPES[self._entry_type]
         if default_value is None:
-            return np.empty(shape, dtype=np.float64)
-        return np.full(shape, default_value, dtype=np.float64)
+            return np.empty(shape, dtype=dtype)
+        return np.full(shape, default_value, dtype=dtype)
+
+    # ---- plan acquisition: flatten + compile, or a plan-cache hit ----
+    def _options_key(self):
+        return (self._resolve_device(), self._use_graph, self._kernel_policy, self._hoist, self._microtree,
+                self._lanes, self._branches, self._mem_limit_bytes)
+
+    def _cast_leaves(self, leaf_data):
+        """What the reference's `create_tensor(shape, value)` does to the leaf values for this entry type."""
+        et = self._entry_type
+        if et == "float32":
+            return leaf_data.astype(np.float32).astype(np.float64)
+        if et == "float16":
+            return leaf_data.astype(np.float16).astype(np.float64)
+        if et in ("int", "uint"):
+            if not np.all(np.isfinite(leaf_data)):
+                raise ValueError("entry_type %s needs finite weights" % et)
+            out = np.trunc(leaf_data)  # numpy float -> int64 conversion truncates toward zero
+            if et == "uint" and np.any(out < 0):
+                raise ValueError("entry_type uint needs non-negative weights")
+            return out
+        return leaf_data
+
+    def _acquire(self, execution_plan):
+        """Returns (compiled, cache_hit).  The leaf values are always re-read from the caller's tensors."""
+        options = self._options_key()
+        if self._plan_cache:
+            entry = PLAN_CACHE.lookup(execution_plan, options)
+            if entry is not None:
+                compiled = entry["compiled"]
+                data = rebuild_leaf_data(execution_plan, compiled.flat)
+                if data is not None:
+                    compiled.flat = dataclasses.replace(compiled.flat, leaf_data=self._cast_leaves(np.ascontiguousarray(data)))
+                    return compiled, True
+                PLAN_CACHE.drop(execution_plan, options)
+        flat = flatten_plan(execution_plan)  # leaves are built through a buffer-backed create_tensor
+        flat = dataclasses.replace(flat, leaf_data=self._cast_leaves(flat.leaf_data))
+        compiled = CompiledPlan(flat, device=options[0], use_graph=self._use_graph,
+                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
+                                use_microtree=self._microtree, slice_lanes=self._lanes,
+                                dag_branches=self._branches, mem_limit_bytes=self._mem_limit_bytes)
+        if self._plan_cache:
+            PLAN_CACHE.store(execution_plan, options, compiled)
+        return compiled, False
+
+    def _done_with(self, compiled, failed=False):
+        if not self._plan_cache:
+            compiled.close()
+        elif failed:
+            compiled.release_device()
+        else:
+            PLAN_CACHE.after_call(compiled)
 
     # ---- the primary entry (base_api.py:17-28, called from execution.py:136) ----
     def contract_sliced(self, execution_plan, num_slice_limit=None):
-        if self._entry_type == "bigint":
-            return self._contract_exact(execution_plan, num_slice_limit)
+        if self._entry_type in ("bigint", "int", "uint"):
+            exact = self._contract_exact(execution_plan, num_slice_limit)
+            if self._entry_type == "bigint":
+                return exact
+            wrapped = exact % (1 << 64)  # numpy's integer arithmetic wraps modulo 2^64
+            if self._entry_type == "uint":
+                return np.uint64(wrapped)
+            return np.int64(wrapped - (1 << 64) if wrapped >= (1 << 63) else wrapped)
         t0 = time.perf_counter()
-        flat = flatten_plan(execution_plan)  # leaves are built through a buffer-backed create_tensor
         rank, world = self._rank_world()
-        compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
-                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
-                                use_microtree=self._microtree, slice_lanes=self._lanes,
-                                dag_branches=self._branches)
+        compiled, hit = self._acquire(execution_plan)
+        failed = True
         try:
             t1 = time.perf_counter()
-            compiled.upload()
-            t2 = time.perf_counter()
             total = compiled.num_slices
             if num_slice_limit is not None:
                 total = min(total, int(num_slice_limit))  # itertools.islice(slices, N), base_api.py:23-24
             count = 0 if rank >= total else (total - rank + world - 1) // world
-            partial = compiled.run_interruptible(first=rank if count else 0, count=count, stride=world)
+            partial, error = 0.0, None
+            try:
+                compiled.update_leaves()
+                t2 = time.perf_counter()
+                partial = compiled.run_interruptible(first=rank if count else 0, count=count, stride=world)
+            except BaseException as exc:  # noqa: BLE001  (re-raised below, on every rank)
+                error = self._give_up_if_unsliceable(exc, compiled)
+                t2 = time.perf_counter()
             t3 = time.perf_counter()
-            result = self._all_reduce(partial) if world > 1 else partial
+            result = self._combine(partial, error) if world > 1 else self._raise_or(partial, error)
+            failed = False
             self.last_stats = {
                 "flatten_compile_s": t1 - t0, "upload_s": t2 - t1, "run_s": t3 - t2,
                 "device_ms": compiled.interruptible_stats["device_ms"],
                 "launches": compiled.interruptible_stats["launches"],
-                "h2d_bytes": int(flat.leaf_data.nbytes), "d2h_bytes": 32,
+                "h2d_bytes": int(compiled.flat.leaf_data.nbytes), "d2h_bytes": 32,
                 "peak_bytes": compiled.peak_bytes, "slices": total, "rank": rank, "world": world,
+                "plan_cache_hit": hit,
             }
         finally:
-            compiled.close()
-        return np.float64(result)
+            self._done_with(compiled, failed)
+        et = self._entry_type
+        with np.errstate(over="ignore"):  # a count beyond the entry type's range is inf there, as in the reference
+            return np.float32(result) if et == "float32" else np.float16(result) if et == "float16" else np.float64(result)
 
-    # ---- exact counts (entry_type = bigint) ----
+    # ---- exact counts (entry_type = bigint, int, uint) ----
     def _contract_exact(self, execution_plan, num_slice_limit=None):
-        """Exact integer result, any magnitude: one float64 pass sizes the answer, then the same compiled
-        plan runs once per prime p < 2^23 with every kernel reducing modulo p (all sums stay below 2^53, so
-        FP64 arithmetic is exact), and the residues are combined by CRT.  Primes are added until the
-        reconstruction is stable and agrees with the float64 estimate."""
-        import dataclasses
+        """Exact integer result, any magnitude: the same compiled plan runs once per prime p < 2^23 with every
+        kernel reducing modulo p (all sums stay below 2^53, so FP64 arithmetic is exact), and the residues are
+        combined by CRT into the symmetric range (-M/2, M/2].  How many primes: for non-negative tensors one
+        float64 pass sizes the answer (no cancellation, so the estimate is good to ~1e-12) and primes are added
+        until the reconstruction is stable and agrees with it; with mixed signs the float64 pass can be
+        arbitrarily far off, so the count comes from the a-priori bound  |result| <= prod_t ||tensor_t||_1."""
         import math
 
         t0 = time.perf_counter()
-        flat = flatten_plan(execution_plan)
-        if not np.all(np.isfinite(flat.leaf_data)) or not np.array_equal(flat.leaf_data, np.rint(flat.leaf_data)) \
-                or np.any(np.abs(flat.leaf_data) >= 2.0 ** 53):
-            raise ValueError("entry_type bigint needs integer-valued tensors (weights must be integers)")
         rank, world = self._rank_world()
-        compiled = CompiledPlan(flat, device=self._resolve_device(), use_graph=self._use_graph,
-                                kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
-                                use_microtree=self._microtree, slice_lanes=self._lanes,
-                                dag_branches=self._branches)
+        compiled, hit = self._acquire(execution_plan)
+        failed = True
         try:
+            leaves = compiled.flat.leaf_data
+            if not np.all(np.isfinite(leaves)) or not np.array_equal(leaves, np.rint(leaves)) \
+                    or np.any(np.abs(leaves) >= 2.0 ** 53):
+                raise ValueError("entry_type %s needs integer-valued tensors (weights must be integers)" % self._entry_type)
             total = compiled.num_slices
             if num_slice_limit is not None:
                 total = min(total, int(num_slice_limit))
             count = 0 if rank >= total else (total - rank + world - 1) // world
             first = rank if count else 0
+            launches = 0
 
             def one_pass(leaf_data, modulus):
-                compiled.flat = dataclasses.replace(flat, leaf_data=np.ascontiguousarray(leaf_data))
-                compiled.upload()
-                compiled.set_modulus(modulus)
-                partial = compiled.run_interruptible(first=first, count=count, stride=world)
-                return self._all_reduce(partial) if world > 1 else partial
+                nonlocal launches
+                partial, error = 0.0, None
+                try:
+                    compiled.update_leaves(leaf_data)
+                    compiled.set_modulus(modulus)
+                    partial = compiled.run_interruptible(first=first, count=count, stride=world)
+                    launches += compiled.interruptible_stats["launches"]
+                except BaseException as exc:  # noqa: BLE001
+                    error = self._give_up_if_unsliceable(exc, compiled)
+                return self._combine(partial, error) if world > 1 else self._raise_or(partial, error)
 
-            estimate = float(one_pass(flat.leaf_data, 0))
-            if math.isfinite(estimate):
-                bits = math.log2(abs(estimate) + 1.0) + 4.0
-            else:  # beyond float64: a-priori bound, the product over tensors of their 1-norms
-                bits = 4.0
-                for l in range(flat.n_leaves):
-                    off = int(flat.leaf_data_offset[l])
-                    bits += math.log2(max(float(np.abs(flat.leaf_data[off: off + (1 << int(flat.leaf_rank[l]))]).sum()), 1.0))
+            flat = compiled.flat
+            bound_bits = 2.0  # a-priori: |result| <= product over tensors of their 1-norms
+            for l in range(flat.n_leaves):
+                off = int(flat.leaf_data_offset[l])
+                bound_bits += math.log2(max(float(np.abs(leaves[off: off + (1 << int(flat.leaf_rank[l]))]).sum()), 1.0))
+            prime_bits = math.log2(EXACT_PRIMES[-1])
+            nonneg = bool(np.all(leaves >= 0))
+            estimate = None
+            if nonneg:
+                estimate = float(one_pass(leaves, 0))
+                if not math.isfinite(estimate):
+                    estimate = None
+            if estimate is not None:
+                need = max(1, math.ceil((math.log2(abs(estimate) + 1.0) + 4.0) / prime_bits))
+            else:
+                need = max(1, math.ceil((bound_bits + 1.0) / prime_bits))  # +1: the symmetric range
+            if need > len(EXACT_PRIMES):
+                raise OverflowError("count needs more than %d primes" % len(EXACT_PRIMES))
             residues, moduli = [], []
             value, passes = None, 0
-            need = max(1, math.ceil(bits / math.log2(EXACT_PRIMES[-1])))
-            while True:
+            while value is None:
                 if len(moduli) >= len(EXACT_PRIMES):
                     raise OverflowError("count needs more than %d primes" % len(EXACT_PRIMES))
                 p = EXACT_PRIMES[len(moduli)]
-                r = one_pass(np.mod(flat.leaf_data, p), p)
+                r = one_pass(np.mod(leaves, p), p)
                 passes += 1
                 if r != int(r) or not (0 <= r < p * max(world, 1)):
                     raise RuntimeError("exact mode: residue %r is not an integer below the modulus" % r)
@@ -368,23 +589,33 @@ class B200API:
                 moduli.append(p)
                 if len(moduli) < need:
                     continue
-                x = crt(residues, moduli)
                 m = math.prod(moduli)
-                if x > m // 2 and (not math.isfinite(estimate) or estimate < 0):
-                    x -= m  # symmetric range for negative totals
-                # stable (the last prime did not change the reconstruction) and consistent with the float64 pass
-                prev = crt(residues[:-1], moduli[:-1]) if len(moduli) > 1 else None
-                if prev is not None and prev > math.prod(moduli[:-1]) // 2 and x < 0:
-                    prev -= math.prod(moduli[:-1])
-                close = (not math.isfinite(estimate)) or abs(x - estimate) <= 1e-6 * abs(estimate) + 1.0
-                if close and (prev == x or len(moduli) == 1 and abs(x) < m // 4):
-                    value = x
+                x = crt(residues, moduli)
+                if x > m // 2:
+                    x -= m  # symmetric range (-M/2, M/2]
+                if estimate is None:
+                    value = x  # M > 2 * bound: the symmetric representative IS the result
                     break
+                # non-negative tensors: stable (one more prime does not change it) and consistent with float64
+                if len(moduli) > 1:
+                    m1 = math.prod(moduli[:-1])
+                    prev = crt(residues[:-1], moduli[:-1])
+                    if prev > m1 // 2:
+                        prev -= m1
+                else:
+                    prev = x if abs(x) < m // 4 else None
+                if prev == x and abs(x - estimate) <= 1e-6 * abs(estimate) + 1.0:
+                    value = x
+            failed = False
             self.last_stats = {"exact_passes": passes, "primes": list(moduli), "float_estimate": estimate,
-                               "seconds": time.perf_counter() - t0, "slices": total, "rank": rank, "world": world,
-                               "launches": compiled.interruptible_stats["launches"]}
+                               "bound_bits": bound_bits, "seconds": time.perf_counter() - t0, "slices": total,
+                               "rank": rank, "world": world, "launches": launches, "plan_cache_hit": hit}
         finally:
-            compiled.close()
+            try:
+                compiled.set_modulus(0)
+            except Exception:
+                pass
+            self._done_with(compiled, failed)
         return value
 
     # ---- secondary entries ----
@@ -401,7 +632,7 @@ class B200API:
         try:
             value = self.contract_sliced(plan)
             # 0-d array so `result[tuple()]` works; exact mode keeps the Python int (object dtype)
-            return np.array(value, dtype=object if self._entry_type == "bigint" else np.float64)
+            return np.array(value, dtype=self._HOST_DTYPES[self._entry_type])
         finally:
             self._distributed = keep
 
@@ -440,9 +671,12 @@ class B200API:
     def _dist_ready(self) -> bool:
         if not self._distributed:
             return False
-        try:
-            import torch.distributed as dist
+        import sys
 
+        dist = sys.modules.get("torch.distributed")  # never imported => no process group; importing torch costs seconds
+        if dist is None:
+            return False
+        try:
             return dist.is_available() and dist.is_initialized()
         except Exception:
             return False
@@ -454,16 +688,48 @@ class B200API:
             return dist.get_rank(), dist.get_world_size()
         return 0, 1
 
-    def _all_reduce(self, partial: float) -> float:
-        """One all-reduce of a float64 scalar (the only exchange step of the sliced path)."""
+    @staticmethod
+    def _give_up_if_unsliceable(error, compiled):
+        """`execution.run` answers OutOfMemoryError by slicing once more, forever (src/execution.py:133-142).  Past
+        40 slice groups (10^12 slices) more slicing is not an answer: the leaves, tables and slice-invariant tensors
+        alone exceed the limit.  MemoryError ends the loop with "Out of Memory during execution" (execution.py:145-148)."""
+        if isinstance(error, (OutOfMemoryError, _oom_class())) and compiled.flat.n_slice_groups >= 40:
+            return MemoryError("b200 tensor library: the plan does not fit the device memory limit at any slicing (%s)" % error)
+        return error
+
+    @staticmethod
+    def _raise_or(value, error):
+        if error is not None:
+            raise error
+        return value
+
+    def _combine(self, partial: float, error) -> float:
+        """The one exchange step of the sliced path: an all-reduce (SUM) of [partial count, OOM flag, timeout
+        flag, other-error flag].  The flags make failures collective: free memory and SIGALRM timing differ
+        per GPU / process, and a rank that left alone would leave its peers blocked in the all-reduce — or,
+        after `execution.run` re-sliced only on that rank (src/execution.py:140-142), summing partials of
+        different slicings.  Every rank raises the same class, so all of them re-slice (or stop) together."""
         import torch
         import torch.distributed as dist
 
+        oom = error is not None and (isinstance(error, _oom_class()) or isinstance(error, OutOfMemoryError))
+        timeout = error is not None and isinstance(error, TimeoutError)
+        other = error is not None and not oom and not timeout
         backend = dist.get_backend()
         dev = torch.device("cuda", self._resolve_device()) if backend == "nccl" else torch.device("cpu")
-        t = torch.tensor([partial], dtype=torch.float64, device=dev)
+        t = torch.tensor([0.0 if error is not None else partial, float(oom), float(timeout), float(other)],
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        total, n_oom, n_timeout, n_other = (float(x) for x in t.tolist())
+        if error is not None:
+            raise error
+        if n_other > 0:
+            raise RuntimeError("b200 tensor library: %d other rank(s) failed during contraction" % int(n_other))
+        if n_timeout > 0:
+            raise TimeoutError("b200 tensor library: %d other rank(s) timed out" % int(n_timeout))
+        if n_oom > 0:
+            raise _oom_class()("b200 tensor library: %d other rank(s) ran out of device memory" % int(n_oom))
+        return total
 
 
 B200_APIS = {"b200": B200API}

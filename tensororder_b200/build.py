@@ -9,7 +9,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libtob200.so")
 SOURCES = ["tob_compile.cpp", "tob_kernels.cu", "tob_exec.cu"]
-HEADERS = ["tob_internal.h", "tob_kernels.cuh", os.path.join("..", "..", "include", "tob200.h")]
+HEADERS = ["tob_internal.h", "tob_kernels.cuh", "tob_dispatch_table.h", os.path.join("..", "..", "include", "tob200.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

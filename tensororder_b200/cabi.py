@@ -50,8 +50,14 @@ SYMBOLS = {
     "tob_plan_num_slices": (c_uint64, [c_void_p]),
     "tob_plan_describe": (c_int64, [c_void_p, c_char_p, c_int64]),
     "tob_plan_upload": (c_int32, [c_void_p, POINTER(c_double), c_int64]),
+    "tob_plan_update_leaves": (c_int32, [c_void_p, POINTER(c_double), c_int64]),
+    "tob_plan_release": (c_int32, [c_void_p]),
+    "tob_pool_trim": (c_int32, [c_int32]),
     "tob_plan_run": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_double)]),
     "tob_plan_run_ex": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, c_double, c_int32, POINTER(c_double)]),
+    "tob_plan_run_async": (c_int32, [c_void_p, c_uint64, c_uint64, c_uint64, c_double, c_int32, c_void_p]),
+    "tob_plan_join": (c_int32, [c_void_p, c_void_p]),
+    "tob_plan_wait": (c_int32, [c_void_p, POINTER(c_double)]),
     "tob_plan_last_ms": (c_double, [c_void_p]),
     "tob_plan_last_issue_ms": (c_double, [c_void_p]),
     "tob_plan_last_launches": (c_int64, [c_void_p]),
@@ -67,6 +73,10 @@ SYMBOLS = {
     "tob_tensordot_host": (c_int32, [POINTER(c_double), c_int32, POINTER(c_double), c_int32, POINTER(c_int32),
                                      POINTER(c_int32), c_int32, POINTER(c_double)]),
     "tob_permute_device": (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32), c_void_p, POINTER(c_float)]),
+    "tob_tuning_set": (c_int32, [c_char_p, c_double]),
+    "tob_tuning_get": (c_int32, [c_char_p, POINTER(c_double)]),
+    "tob_gemm_time_model_us": (c_double, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "tob_warm": (c_int32, [c_int32]),
     "tob_device_count": (c_int32, []),
     "tob_version": (c_char_p, []),
     "tob_last_error": (c_char_p, []),

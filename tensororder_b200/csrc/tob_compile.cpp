@@ -19,67 +19,122 @@
 #include <sstream>
 #include <chrono>
 
+#include "tob_dispatch_table.h"
 #include "tob_internal.h"
 
 namespace tob {
 
 static const int kMaxRank = 40;       // 2^40 doubles is far beyond 180 GB; guards the bit math
 static const int64_t kAlign = 32;     // arena alignment in doubles (256 B)
-static const int kNumSMs = 148;
+// SM count of the device the plans run on: 148 on a full B200; tob_exec.cu replaces it with the queried
+// cudaDevAttrMultiProcessorCount (other sm_100 parts, MIG slices) before the first plan is compiled
+static int g_num_sms = 148;
+int num_sms() { return g_num_sms; }
+void set_num_sms(int n) { if (n > 0) g_num_sms = n; }
+#define kNumSMs (num_sms())
 
 static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
 // Kernel choice for a canonical join  C[2^(m+n)] = A[2^m x 2^k] . B[2^n x 2^k]^T
 // ------------------------------------------------------------------------------------------------
-int gemm_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("TOB_GEMM_VARIANT");
-        v = e ? atoi(e) : 3;
-    }
-    return v;
+Tuning& tuning() {
+    static Tuning t = {
+        TOB_TUNE_GEMM_MIN_FREE, TOB_TUNE_GEMM_MIN_K, TOB_TUNE_GEMM_MIN_TOTAL, TOB_TUNE_GEMM_SMALLK_MIN_FREE,
+        TOB_TUNE_GEMM_SMALLK_MIN_OUT, TOB_TUNE_T1_MAX_K, TOB_TUNE_T32_MAX_K, TOB_TUNE_T32_MIN_OUT,
+        TOB_TUNE_PERSIST_MAX_K, TOB_TUNE_SM_GFLOPS, TOB_TUNE_ALONE_FRAC, TOB_TUNE_GEMM_FIX_US, TOB_TUNE_REDUCE_GBS,
+        TOB_TUNE_REDUCE_FIX_US, TOB_TUNE_MAX_KSPLIT_LOG2, TOB_TUNE_MIN_K_PER_SPLIT_LOG2, -1};
+    return t;
+}
+
+namespace {
+struct TuneField { const char* key; int Tuning::*i; double Tuning::*d; };
+const TuneField kTuneFields[] = {
+    {"gemm_min_free", &Tuning::gemm_min_free, nullptr}, {"gemm_min_k", &Tuning::gemm_min_k, nullptr},
+    {"gemm_min_total", &Tuning::gemm_min_total, nullptr}, {"gemm_smallk_min_free", &Tuning::gemm_smallk_min_free, nullptr},
+    {"gemm_smallk_min_out", &Tuning::gemm_smallk_min_out, nullptr}, {"t1_max_k", &Tuning::t1_max_k, nullptr},
+    {"t32_max_k", &Tuning::t32_max_k, nullptr}, {"t32_min_out", &Tuning::t32_min_out, nullptr},
+    {"persist_max_k", &Tuning::persist_max_k, nullptr}, {"sm_gflops", nullptr, &Tuning::sm_gflops},
+    {"alone_frac", nullptr, &Tuning::alone_frac}, {"gemm_fix_us", nullptr, &Tuning::gemm_fix_us},
+    {"reduce_gbs", nullptr, &Tuning::reduce_gbs}, {"reduce_fix_us", nullptr, &Tuning::reduce_fix_us},
+    {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
+    {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
+};
+}  // namespace
+
+bool tuning_set(const char* key, double value) {
+    for (const TuneField& f : kTuneFields)
+        if (key && std::string(key) == f.key) {
+            if (f.i) tuning().*(f.i) = (int)value; else tuning().*(f.d) = value;
+            return true;
+        }
+    return false;
+}
+bool tuning_get(const char* key, double* value) {
+    for (const TuneField& f : kTuneFields)
+        if (key && std::string(key) == f.key) {
+            *value = f.i ? (double)(tuning().*(f.i)) : tuning().*(f.d);
+            return true;
+        }
+    return false;
+}
+
+// A GEMM launch of `blocks` CTAs on `slots` CTA slots: full waves run with every SM shared by its resident CTAs;
+// a last partial wave that leaves each CTA an SM to itself runs faster per CTA (alone_frac of the SM's DMMA rate
+// instead of 1/2), which is what makes a short grid less bad than its wave count says and a split that merely fills
+// more slots less good.  Split-K adds the partials' traffic (written once, read once) and the reduce launch.
+double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c) {
+    const Tuning& T = tuning();
+    const int per_sm = (tm_log2 == 7 && tn_log2 == 6) ? 2 : 1;
+    const double sms = kNumSMs, slots = sms * per_sm;
+    const double blocks = std::ldexp(1.0, (m - tm_log2) + (n - tn_log2) + c);
+    const double ksteps = std::max(1.0, std::ldexp(1.0, k - c - 4));  // K steps of 16
+    const double step_flops = 2.0 * std::ldexp(1.0, tm_log2 + tn_log2 + 4);
+    const double sm_flops_per_us = T.sm_gflops * 1e3;
+    const double step_shared = step_flops / (sm_flops_per_us / per_sm);
+    const double step_alone = step_flops / (sm_flops_per_us * std::min(1.0, per_sm == 2 ? T.alone_frac : 1.0));
+    const double full = std::floor(blocks / slots), rem = blocks - full * slots;
+    double t = full * ksteps * step_shared;
+    if (rem > 0) t += ksteps * (rem <= sms ? step_alone : step_shared);
+    t += T.gemm_fix_us;
+    if (c > 0) t += 16.0 * std::ldexp(1.0, m + n + c) / (T.reduce_gbs * 1e3) + T.reduce_fix_us;
+    return t;
 }
 
 void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
+    const Tuning& T = tuning();
     const int m = op->m, n = op->n, k = op->k;
     op->flops = 2.0 * std::ldexp(1.0, m + n + k);
     op->bytes = 8.0 * (std::ldexp(1.0, m + k) + std::ldexp(1.0, n + k) + std::ldexp(1.0, m + n));
     op->ksplit_log2 = 0;
-    // k >= 4: the DMMA pipeline proper.  1 <= k <= 3 with a large two-sided output (outer-product-like
-    // joins): the same kernel with a zero-filled K step, i.e. a tiled store kernel with full operand
-    // reuse, instead of one thread per output re-reading both rows from L2.
-    const bool gemm_ok = (k >= 4 && m >= 6 && n >= 6 && (m + n + k) >= 20) || (k >= 1 && k <= 3 && m >= 7 && n >= 7 && (m + n) >= 18);
+    // k >= gemm_min_k: the DMMA pipeline proper.  1 <= k < gemm_min_k with a large two-sided output (outer-product-
+    // like joins): the same kernel with a zero-filled K step, i.e. a tiled store kernel with full operand reuse,
+    // instead of one thread per output re-reading both rows from L2.  Thresholds: tob_dispatch_table.h (measured).
+    const bool gemm_ok = (k >= T.gemm_min_k && m >= T.gemm_min_free && n >= T.gemm_min_free && (m + n + k) >= T.gemm_min_total) ||
+                         (k >= 1 && k < T.gemm_min_k && m >= T.gemm_smallk_min_free && n >= T.gemm_smallk_min_free &&
+                          (m + n) >= T.gemm_smallk_min_out);
     if (kernel_policy != 1 && gemm_ok) {
         op->kind = OP_GEMM;
         op->tm_log2 = std::min(m, 7);
-        op->tn_log2 = std::min(n, 7);
-        if (gemm_variant() == 3 && op->tn_log2 == 7) op->tn_log2 = 6;
-        int64_t tiles = (int64_t)1 << ((m - op->tm_log2) + (n - op->tn_log2));
+        op->tn_log2 = std::min(n, 6);  // 128x64 tiles, two CTAs per SM (64x64 when m == 6)
         int ks = 0;
-        // concurrent CTA slots: the 128x64 kernels run two CTAs per SM
-        const int slots = kNumSMs * ((op->tm_log2 == 7 && op->tn_log2 == 6) ? 2 : 1);
-        if (allow_splitk && tiles < 8 * slots) {
-            // short grid: pick the power-of-two K split with the best wave efficiency (blocks / SMs
-            // rounded up), keeping >= 128 K elements per split; ties go to the smaller split
-            // ... and keep the split-K partials (written once, read once: 16 * 2^(m+n+c) bytes at ~5 TB/s)
-            // below ~15 % of the join's own tensor-pipe time: 2^c <= 0.0027 * 2^k
-            double best = -1.0;
-            for (int c = 0; (k - c) >= 7 && c <= 6 && std::ldexp(1.0, c) <= std::max(1.0, 0.0027 * std::ldexp(1.0, k)); c++) {
-                const double blocks = (double)(tiles << c);
-                const double waves = blocks / slots;
-                const double eff = waves / std::ceil(waves) - 0.004 * c;
-                if (eff > best + 1e-9) { best = eff; ks = c; }
+        if (allow_splitk) {
+            // the power-of-two K split with the shortest modelled time (gemm_time_model_us); ties go to the smaller split
+            double best = gemm_time_model_us(m, n, k, op->tm_log2, op->tn_log2, 0);
+            for (int c = 1; c <= T.max_ksplit_log2 && (k - c) >= T.min_k_per_split_log2; c++) {
+                const double t = gemm_time_model_us(m, n, k, op->tm_log2, op->tn_log2, c);
+                if (t < best * 0.97) { best = t; ks = c; }
             }
+            if (T.force_ksplit_log2 >= 0) ks = std::max(0, std::min(T.force_ksplit_log2, k - 4));
         }
         op->ksplit_log2 = ks;
         return;
     }
     op->kind = OP_GENERIC;
     const int outs = m + n;
-    if (k <= 6) {
+    if (k <= T.t1_max_k) {
         op->threads_per_out = 1;
-    } else if (outs >= 12 && k <= 11) {
+    } else if (outs >= T.t32_min_out && k <= T.t32_max_k) {
         op->threads_per_out = 32;
     } else {
         op->threads_per_out = 256;
@@ -619,7 +674,11 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
     // Two slices in flight (own arena + workspace + stream each) when that costs at most 2 GiB extra: the
     // launch-bound stretches of one slice then overlap the GEMMs of the other.  opt.slice_lanes: 0 auto, 1, 2.
     const int want_lanes = opt.slice_lanes;
-    const bool cheap = (P->arena_doubles + P->ws_doubles) * 8 <= ((int64_t)2 << 30);
+    bool cheap = (P->arena_doubles + P->ws_doubles) * 8 <= ((int64_t)2 << 30);
+    // under a byte budget (tob_options.mem_limit_bytes, e.g. the b200_mem slicer's --mem_limit) the second lane is the
+    // first thing to go: it must not be what pushes a plan over the limit and triggers one more slice
+    if (opt.mem_limit_bytes > 0 && 8 * (P->leaf_doubles + 2 * (P->arena_doubles + P->ws_doubles)) + (1 << 17) > opt.mem_limit_bytes)
+        cheap = false;
     P->lanes = (S > 0 && (want_lanes == 2 || (want_lanes == 0 && cheap))) ? 2 : 1;
     P->branches = std::max(schedule_branches(&P->invariant_ops, max_branches), schedule_branches(&P->slice_ops, max_branches));
     lap("dag schedule");

@@ -75,6 +75,7 @@ struct tob_plan {
     size_t h_block_size = 0;
     DevState* h_state = nullptr;   // upload slots, one per lane
     double* h_readback = nullptr;  // result slot
+    double* h_leaves = nullptr;    // pinned mirror of the leaf region (tob_plan_update_leaves refills it)
     bool has_terms = false;
     double last_ms = 0, last_issue_ms = 0;
     int64_t last_launches = 0;
@@ -87,6 +88,11 @@ struct tob_plan {
     double slice_flops = 0, invariant_flops = 0;
     bool time_gemm = false;
     bool in_flight = false;  // a run or profile pass has been issued and not yet waited for
+    // tob_plan_run_async -> tob_plan_wait
+    bool pending = false;
+    int pending_launches = 0;
+    size_t pending_gemm = 0;
+    cudaEvent_t ev_after = nullptr;  // orders an async run after the caller's stream
     double modulus = 0.0;  // exact mode: prime modulus (< 2^23), 0 = float64 arithmetic
 };
 
@@ -115,6 +121,7 @@ std::vector<Block> g_free_blocks;
 std::vector<StreamSet> g_free_streams;
 const size_t kMaxCachedBlock = (size_t)2 << 30;
 const size_t kMaxCachedTotal = (size_t)8 << 30;
+const size_t kMaxCachedPinned = (size_t)256 << 20;  // idle pinned host memory kept for reuse
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -187,9 +194,25 @@ void pool_release(const Block& b) {
         cudaFree(b.ptr);
         return;
     }
+    if (b.pinned && b.size > kMaxCachedPinned / 4) {
+        cudaFreeHost(b.ptr);
+        return;
+    }
     std::lock_guard<std::mutex> lock(g_pool_mu);
     g_free_blocks.push_back(b);
-    if (!b.pinned) pool_trim_locked(b.device, kMaxCachedTotal);
+    if (!b.pinned) {
+        pool_trim_locked(b.device, kMaxCachedTotal);
+        return;
+    }
+    size_t pinned_total = 0;  // idle pinned blocks: oldest go first once the cap is exceeded
+    for (const Block& f : g_free_blocks)
+        if (f.pinned) pinned_total += f.size;
+    for (size_t i = 0; i < g_free_blocks.size() && pinned_total > kMaxCachedPinned;) {
+        if (!g_free_blocks[i].pinned) { i++; continue; }
+        pinned_total -= g_free_blocks[i].size;
+        cudaFreeHost(g_free_blocks[i].ptr);
+        g_free_blocks.erase(g_free_blocks.begin() + i);
+    }
 }
 
 cudaError_t streams_acquire(int device, StreamSet* out) {
@@ -272,7 +295,35 @@ void tob_default_options(tob_options* opt) {
 }
 
 const char* tob_last_error(void) { return g_error.c_str(); }
+
+int tob_tuning_set(const char* key, double value) {
+    if (tuning_set(key, value)) return TOB_OK;
+    set_error(std::string("unknown tuning key: ") + (key ? key : "(null)"));
+    return TOB_E_INVALID;
+}
+double tob_gemm_time_model_us(int32_t m, int32_t n, int32_t k, int32_t tm_log2, int32_t tn_log2, int32_t c) {
+    return gemm_time_model_us(m, n, k, tm_log2, tn_log2, c);
+}
+int tob_tuning_get(const char* key, double* value) {
+    if (value && tuning_get(key, value)) return TOB_OK;
+    set_error(std::string("unknown tuning key: ") + (key ? key : "(null)"));
+    return TOB_E_INVALID;
+}
 const char* tob_version(void) { return "tob200 0.1 (sm_100a)"; }
+
+int tob_warm(int32_t device) {
+    int rc = ensure_device(device);  // context + kernel attributes
+    if (rc != TOB_OK) return rc;
+    CUDA_TRY(cudaFree(nullptr));
+    // first-use costs that would otherwise land in the first contraction: a small pinned + device block and a stream set
+    Block hb, db;
+    if (pool_acquire(1 << 20, device, true, &hb) == cudaSuccess) pool_release(hb);
+    if (pool_acquire(8 << 20, device, false, &db) == cudaSuccess) pool_release(db);
+    StreamSet ss;
+    if (streams_acquire(device, &ss) == cudaSuccess) streams_release(ss);
+    cudaGetLastError();
+    return TOB_OK;
+}
 
 int tob_device_count(void) {
     int n = 0;
@@ -280,9 +331,22 @@ int tob_device_count(void) {
     return n;
 }
 
+// the SM count feeds the compiler's wave model and the persistent grids; queried once, without creating a context
+static void query_num_sms(int device) {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int n = 0, sms = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return; }
+    if (device < 0 || device >= n) device = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) set_num_sms(sms);
+    else cudaGetLastError();
+}
+
 int tob_plan_create(const tob_plan_desc* desc, const tob_options* opt, tob_plan** out) {
     if (!out) { set_error("out is NULL"); return TOB_E_INVALID; }
     *out = nullptr;
+    query_num_sms(opt ? opt->device : 0);
     tob_plan* p = new tob_plan();
     std::string err;
     int rc = compile(desc, opt, &p->prog, &err);
@@ -349,9 +413,12 @@ static void release_device(tob_plan* p) {
     pool_release(Block{p->h_block, p->h_block_size, p->device, true});
     for (cudaEvent_t e : p->gemm_events) cudaEventDestroy(e);
     p->gemm_events.clear();
+    event_release(p->device, p->ev_after);
+    p->ev_after = nullptr;
+    p->pending = false;
     p->d_block = nullptr; p->h_block = nullptr;
     p->d_term_start = nullptr; p->d_id_bit = nullptr; p->d_addr_bit = nullptr;
-    p->h_state = nullptr; p->h_readback = nullptr;
+    p->h_state = nullptr; p->h_readback = nullptr; p->h_leaves = nullptr;
     p->d_micro_ops.clear();
     p->d_micro_start.clear();
     p->uploaded = false;
@@ -369,6 +436,21 @@ void tob_plan_destroy(tob_plan* p) {
 
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// leaves permuted on the host into canonical order (LeafInfo::src_bit), zero-padded to the arena alignment
+static void fill_leaves(const Program& G, const double* leaf_data, double* h_leaves) {
+    for (const LeafInfo& Lf : G.leaves) {
+        const int64_t n = (int64_t)1 << Lf.rank;
+        const double* src = leaf_data + Lf.src_offset;
+        double* dst = h_leaves + Lf.dev_offset;
+        for (int64_t e = 0; e < n; e++) {
+            int64_t sidx = 0;
+            for (int q = 0; q < Lf.rank; q++) sidx |= ((e >> q) & 1) << Lf.src_bit[q];
+            dst[e] = src[sidx];
+        }
+        for (int64_t e = n; e < (int64_t)align_up((size_t)n, 32); e++) dst[e] = 0.0;
+    }
 }
 
 int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
@@ -548,18 +630,8 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         }
         if (!mp.cta_start.empty()) memcpy(h + o_mstart[w], mp.cta_start.data(), mp.cta_start.size() * sizeof(int32_t));
     }
-    double* h_leaves = reinterpret_cast<double*>(h + o_leaves);
-    for (const LeafInfo& Lf : G.leaves) {
-        const int64_t n = (int64_t)1 << Lf.rank;
-        const double* src = leaf_data + Lf.src_offset;
-        double* dst = h_leaves + Lf.dev_offset;
-        for (int64_t e = 0; e < n; e++) {
-            int64_t sidx = 0;
-            for (int q = 0; q < Lf.rank; q++) sidx |= ((e >> q) & 1) << Lf.src_bit[q];
-            dst[e] = src[sidx];
-        }
-        for (int64_t e = n; e < (int64_t)align_up((size_t)n, 32); e++) dst[e] = 0.0;
-    }
+    p->h_leaves = reinterpret_cast<double*>(h + o_leaves);
+    fill_leaves(G, leaf_data, p->h_leaves);
     const double t_fill = now_ms();
     // ---- ONE pinned host->device copy: state, tables, micro programs, leaves ----
     p->in_flight = true;
@@ -570,6 +642,41 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         fprintf(stderr, "[tob] upload: ensure_device %.3f  streams+tables %.3f  alloc %.3f  fill %.3f  h2d+sync %.3f ms (%zu B)\n",
                 t_dev - t_begin, t_tables - t_dev, t_alloc - t_tables, t_fill - t_alloc, now_ms() - t_fill, prefix_bytes);
     p->uploaded = true;
+    return TOB_OK;
+}
+
+int tob_plan_update_leaves(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
+    if (!p || !leaf_data) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (!p->uploaded) return tob_plan_upload(p, leaf_data, n_doubles);
+    if (n_doubles != p->prog.src_leaf_len) { set_error("leaf buffer length does not match the plan"); return TOB_E_INVALID; }
+    int rc = ensure_device(p->device);
+    if (rc != TOB_OK) return rc;
+    fill_leaves(p->prog, leaf_data, p->h_leaves);
+    p->in_flight = true;
+    CUDA_TRY(cudaMemcpyAsync(p->d_leaves, p->h_leaves, (size_t)p->prog.leaf_doubles * 8, cudaMemcpyHostToDevice, p->lane[0].stream));
+    CUDA_TRY(cudaStreamSynchronize(p->lane[0].stream));
+    p->in_flight = false;
+    return TOB_OK;
+}
+
+int tob_plan_release(tob_plan* p) {
+    if (!p) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (p->uploaded || p->lane[0].own_stream) {
+        cudaSetDevice(p->device);
+        release_device(p);
+    }
+    return TOB_OK;
+}
+
+int tob_pool_trim(int32_t device) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = g_free_blocks.size(); i-- > 0;) {
+        const Block b = g_free_blocks[i];
+        if (device >= 0 && !b.pinned && b.device != device) continue;
+        if (!b.pinned) cudaSetDevice(b.device);
+        if (b.pinned) cudaFreeHost(b.ptr); else cudaFree(b.ptr);
+        g_free_blocks.erase(g_free_blocks.begin() + i);
+    }
     return TOB_OK;
 }
 
@@ -683,10 +790,44 @@ int tob_plan_run(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, d
     return tob_plan_run_ex(p, first, count, stride, 0.0, 0, result);
 }
 
+static int run_issue(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double initial, int32_t flags,
+                     bool async, cudaStream_t after);
+static int run_finish(tob_plan* p, double* result);
+
 int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double initial, int32_t flags,
                     double* result) {
     if (!p || !result) { set_error("NULL argument"); return TOB_E_INVALID; }
+    int rc = run_issue(p, first, count, stride, initial, flags, false, nullptr);
+    if (rc != TOB_OK) return rc;
+    return run_finish(p, result);
+}
+
+int tob_plan_run_async(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double initial, int32_t flags,
+                       void* after_stream) {
+    if (!p) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (count > (uint64_t)kMaxResults) {
+        set_error("tob_plan_run_async: at most " + std::to_string(kMaxResults) + " slices per call");
+        return TOB_E_INVALID;
+    }
+    return run_issue(p, first, count, stride, initial, flags, true, (cudaStream_t)after_stream);
+}
+
+int tob_plan_join(tob_plan* p, void* stream) {
+    if (!p || !p->pending) { set_error("tob_plan_join: no run in flight"); return TOB_E_INVALID; }
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, p->lane[0].ev_b, 0));
+    return TOB_OK;
+}
+
+int tob_plan_wait(tob_plan* p, double* result) {
+    if (!p || !result) { set_error("NULL argument"); return TOB_E_INVALID; }
+    if (!p->pending) { set_error("tob_plan_wait: no run in flight"); return TOB_E_INVALID; }
+    return run_finish(p, result);
+}
+
+static int run_issue(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride, double initial, int32_t flags,
+                     bool async, cudaStream_t after) {
     if (!p->uploaded) { set_error("tob_plan_upload has not been called"); return TOB_E_INVALID; }
+    if (p->pending) { set_error("a run is already in flight on this plan (tob_plan_wait first)"); return TOB_E_INVALID; }
     const uint64_t nslices = tob_plan_num_slices(p);
     if (count > 0 && (first >= nslices || first + (count - 1) * stride >= nslices)) {
         set_error("slice range exceeds the number of slices");
@@ -738,6 +879,11 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
 
     const double t_issue0 = now_ms();
     p->in_flight = true;
+    if (after && after != L0.stream) {  // start behind everything already enqueued on the caller's stream
+        if (!p->ev_after) CUDA_TRY(event_acquire(p->device, &p->ev_after));
+        CUDA_TRY(cudaEventRecord(p->ev_after, after));
+        CUDA_TRY(cudaStreamWaitEvent(L0.stream, p->ev_after, 0));
+    }
     CUDA_TRY(cudaEventRecord(L0.ev_a, L0.stream));
     uint64_t done = 0;
     bool first_batch = true;
@@ -813,13 +959,24 @@ int tob_plan_run_ex(tob_plan* p, uint64_t first, uint64_t count, uint64_t stride
     CUDA_TRY(cudaEventRecord(L0.ev_b, L0.stream));
     CUDA_TRY(cudaMemcpyAsync(p->h_readback, p->d_acc, sizeof(double), cudaMemcpyDeviceToHost, L0.stream));
     p->last_issue_ms = now_ms() - t_issue0;  // host time spent issuing the run (everything before the final wait)
+    p->pending = true;
+    p->pending_launches = launches;
+    p->pending_gemm = n_gemm;
+    (void)async;
+    return TOB_OK;
+}
+
+static int run_finish(tob_plan* p, double* result) {
+    Lane& L0 = p->lane[0];
+    p->pending = false;
     CUDA_TRY(cudaStreamSynchronize(L0.stream));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, L0.ev_a, L0.ev_b));
     p->last_ms = ms;
-    p->last_launches = launches;
+    p->last_launches = p->pending_launches;
     p->last_gemm_ms = 0;
     p->last_gemm_flops = 0;
+    const size_t n_gemm = p->pending_gemm;
     for (size_t i = 0; i < n_gemm; i++) {
         float g = 0;
         CUDA_TRY(cudaEventElapsedTime(&g, p->gemm_events[2 * i], p->gemm_events[2 * i + 1]));

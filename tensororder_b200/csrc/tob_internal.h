@@ -111,7 +111,24 @@ int schedule_branches(std::vector<Op>* list, int max_branches);
 
 void set_error(const std::string& msg);
 
-// Experiment switch for the 128x128 DMMA GEMM (see tob_kernels.cu); 3 = prefer 128x64 tiles, 2 CTAs per SM.
-int gemm_variant();
+// SM count used for grid sizing and the split-K wave model (default 148; queried from the device when one exists)
+int num_sms();
+void set_num_sms(int n);
+
+// Per-join dispatch parameters: defaults come from the measured table tob_dispatch_table.h (generated by
+// tools/fit_dispatch.py); tob_tuning_set overrides single values at run time (experiments, the fit itself).
+struct Tuning {
+    int gemm_min_free, gemm_min_k, gemm_min_total, gemm_smallk_min_free, gemm_smallk_min_out;
+    int t1_max_k, t32_max_k, t32_min_out;
+    int persist_max_k;
+    double sm_gflops, alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us;
+    int max_ksplit_log2, min_k_per_split_log2;
+    int force_ksplit_log2;  // >= 0: experiments only — every split-capable GEMM uses this split
+};
+Tuning& tuning();
+bool tuning_set(const char* key, double value);
+bool tuning_get(const char* key, double* value);
+// Modelled duration (microseconds) of a GEMM-kernel join with K split 2^c ways (choose_kernel minimises it).
+double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c);
 
 }  // namespace tob

@@ -833,19 +833,13 @@ constexpr size_t gemm_smem_bytes() {
     return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (TK + 4) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8;
 }
 
-// 128x128 variants (TOB_GEMM_VARIANT): 0 = 8 warps TK16 x4 stages; 1 = 8 warps TK32 x3 stages (default: fewer
-// CTA barriers per flop); 2 = 16 warps (32x32 warp tiles) TK32 x3 stages.  128x64 runs 2 CTAs per SM.
-#define GEMM_77_A k_gemm_dmma<7, 7, 2, 4, 16, 4, 1>
-#define GEMM_77_B k_gemm_dmma<7, 7, 2, 4, 32, 3, 1>
-#define GEMM_77_C k_gemm_dmma<7, 7, 4, 4, 32, 3, 1>
+// The shipped instantiations (the 128x128, one-producer, bulk-copy and four-producer variants measured in round 1
+// are documented in DESIGN.md §4 and were removed from the build): 128x64 tiles at two CTAs per SM.
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
 #define GEMM_76_P k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2>
-#define GEMM_76_WS k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, true, false>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
-#define GEMM_76_WZ k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
-#define GEMM_76_WZ4 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 4>
 // residue-arithmetic instantiations (entry type bigint)
 #define GEMM_76_X k_gemm_dmma<7, 6, 4, 2, 16, 3, 2, true>
 #define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
@@ -857,27 +851,15 @@ __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* _
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(GEMM_77_A, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 16, 4>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_77_B, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 32, 3>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_77_C, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 7, 32, 3>());
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_WS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_WZ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_WZ4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
@@ -1155,40 +1137,18 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             else if (op.tm_log2 == 6 && op.tn_log2 == 6)
                 GEMM_66_X<<<(unsigned)blocks, 256, gemm_smem_bytes<6, 6, 16, 4>(), stream>>>(p);
             else
-                return cudaErrorInvalidConfiguration;  // 128x128 experiment variants have no exact instantiation
-        } else if (op.tm_log2 == 7 && op.tn_log2 == 7) {
-            const int v = gemm_variant();
-            const bool k32 = (op.k - op.ksplit_log2) >= 5;  // the TK=32 variants need >= 32 K elements per split
-            if (v == 2 && k32)
-                GEMM_77_C<<<(unsigned)blocks, 512, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
-            else if (v >= 1 && k32)
-                GEMM_77_B<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 32, 3>(), stream>>>(p);
-            else
-                GEMM_77_A<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 7, 16, 4>(), stream>>>(p);
+                return cudaErrorInvalidConfiguration;
         } else if (op.tm_log2 == 7 && op.tn_log2 == 6) {
-            // TOB_GEMM_WS: 4 (default) = warp-specialised pipeline, TWO producer warps issuing LDGSTS into a
-            // swizzled 4-stage ring, mbarrier full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
-            // (the producer's issue rate was the limiter: one producer warp gives 33.8-34.1, four spill);
-            // 2/3 = one producer warp (padded 3-stage / swizzled 4-stage ring); 1 = 128-byte bulk copies
-            // (UBLKCP: 2.4x SLOWER, request-bound at one row per request); 0 = CTA-barrier cp.async pipeline.
-            static const int ws = getenv("TOB_GEMM_WS") ? atoi(getenv("TOB_GEMM_WS")) : 4;
-            static const bool persist_small_k = !(getenv("TOB_GEMM_PERSIST") && atoi(getenv("TOB_GEMM_PERSIST")) == 0);
-            static const int persist_k = getenv("TOB_GEMM_PERSIST_K") ? atoi(getenv("TOB_GEMM_PERSIST_K")) : 5;  // log2 of the longest K
-            if (persist_small_k && (op.k - op.ksplit_log2) <= persist_k && blocks > 2ull * 148ull)
-                // K <= 32 per split, more tiles than CTA slots: persistent CTAs prefetch the next tiles
-                GEMM_76_P<<<2 * 148, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
-            else if (ws == 1 && (op.k - op.ksplit_log2) >= 4)
-                GEMM_76_WS<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
-            else if (ws == 4 && (op.k - op.ksplit_log2) >= 8)
+            const Tuning& T = tuning();
+            const int kk = op.k - op.ksplit_log2;  // log2 of the K range one CTA walks
+            if (kk <= T.persist_max_k && blocks > 2ull * (unsigned long long)num_sms())
+                // short K, more tiles than CTA slots (the store-bound joins): persistent CTAs prefetch the next tiles
+                GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+            else if (kk >= 8)
+                // warp-specialised pipeline, TWO producer warps issuing LDGSTS into a swizzled 4-stage ring, mbarrier
+                // full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
                 GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            else if (ws == 4 && (op.k - op.ksplit_log2) >= 6)  // K = 64, 128: the shorter 3-stage ring fills faster
-                GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
-            else if (ws == 5 && (op.k - op.ksplit_log2) >= 6)
-                GEMM_76_WZ4<<<(unsigned)blocks, 384, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            else if ((ws == 3 || (ws == 2 && (op.k - op.ksplit_log2) >= 8)) && (op.k - op.ksplit_log2) >= 6)
-                // swizzled dense rows, 4 stages: +0.2 % (K=65536) .. +1.5 % (K=1024) over the padded 3-stage ring
-                GEMM_76_WZ<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            else if (ws >= 2 && (op.k - op.ksplit_log2) >= 6)
+            else if (kk >= 6)  // K = 64, 128: the shorter 3-stage ring fills faster
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else
                 GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
@@ -1225,7 +1185,7 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         if (outs <= 4096 && op.ksplit_log2 >= 5)
             k_reduce_splits_warp<<<grid_for(outs, 8, cap), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
         else
-            k_reduce_splits<<<grid_for(outs, 256, 148 * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
+            k_reduce_splits<<<grid_for(outs, 256, (unsigned long long)num_sms() * 16), 256, 0, stream>>>(p.ws, p.c, outs, 1 << op.ksplit_log2, p.modp, p.inv_modp);
         (*launches)++;
         e = cudaGetLastError();
     }
@@ -1350,7 +1310,7 @@ cudaError_t launch_permute(const double* in, double* out, int rank, const int32_
         if (!in_tile[q]) { p.rest_out[p.nrest] = (uint8_t)q; p.rest_in[p.nrest] = (uint8_t)src_bit[q]; p.nrest++; }
     const unsigned long long ntiles = 1ull << p.nrest;
     static const int bl_env = getenv("TOB_PERMUTE_BLOCKS") ? atoi(getenv("TOB_PERMUTE_BLOCKS")) : 8;
-    const unsigned blocks = (unsigned)(ntiles < 148ull * bl_env ? ntiles : 148ull * bl_env);
+    const unsigned blocks = (unsigned)(ntiles < (unsigned long long)num_sms() * bl_env ? ntiles : (unsigned long long)num_sms() * bl_env);
     const size_t smem = ((size_t)1 << n) * 8;
     if (rank <= 32) {
         switch (n - 8) {

@@ -96,6 +96,38 @@ except ImportError:  # not built: the Python loop below does the same work
 USE_COMPILED = True  # tests flip this to run both implementations
 
 
+def rebuild_leaf_data(plan, flat: FlatPlan):
+    """Leaf values of `plan` re-read through `Tensor.build()` in the order `flatten_plan` stored them (plan
+    cache hits: the tree walk and the compile are skipped, the caller's tensors are still read on every call).
+    Returns None when the leaves no longer fit the cached structure (the caller then re-flattens)."""
+    network = plan.network
+    if _flatten_fast is not None and USE_COMPILED:
+        try:
+            return _flatten_fast.rebuild_leaves(network, flat.leaf_tensor_index, flat.leaf_rank, flat.leaf_data_offset,
+                                                int(flat.leaf_data.shape[0]))
+        except (IndexError, KeyError, AttributeError, TypeError):
+            return None
+    arena = _LeafArena(max(int(flat.leaf_data.shape[0]), 16))
+    seen = set()
+    try:
+        for j, t in enumerate(flat.leaf_tensor_index):
+            if t in seen:
+                continue
+            seen.add(t)
+            size = 1 << int(flat.leaf_rank[j])
+            built = network[t].build(arena.factory)
+            if getattr(built, "size", size) != size or arena.used != int(flat.leaf_data_offset[j]):
+                return None
+            arena.commit(built, size)
+    except (IndexError, KeyError, AttributeError, TypeError):
+        return None
+    if arena.used != int(flat.leaf_data.shape[0]):
+        return None
+    return arena.buf[: arena.used]
+
+
+
+
 def flatten_plan(plan, tensor_factory=None) -> FlatPlan:
     network = plan.network
     # edge id -> slice group index (non-empty groups only, in order)

@@ -11,8 +11,10 @@ from .api import CompiledPlan
 from .flatten import flatten_plan
 
 
-def plan_peak_bytes(plan) -> int:
-    cp = CompiledPlan(flatten_plan(plan))
+def plan_peak_bytes(plan, mem_limit_bytes: int = 0) -> int:
+    """Device bytes the executor needs for `plan` (host-only compile).  With a budget the compiler drops its
+    optional second slice lane before it would exceed it, exactly as `B200API` compiles under `mem_limit_bytes`."""
+    cp = CompiledPlan(flatten_plan(plan), mem_limit_bytes=int(mem_limit_bytes))
     try:
         return cp.peak_bytes
     finally:
@@ -25,7 +27,7 @@ class B200MemSlicer:
 
     def slice_until(self, plan, memory=None, rank=None, slices=None):
         """Same signature and units as BaseSlicer.slice_until (slicers.py:10-24)."""
-        while memory is not None and memory * 8 < plan_peak_bytes(plan):
+        while memory is not None and memory * 8 < plan_peak_bytes(plan, int(memory * 8)):
             if plan.next_edge_to_slice is None or plan.next_edge_to_slice < 0 or len(plan.groups_to_slice) >= 60:
                 raise RuntimeError("b200_mem slicer: the plan cannot be sliced below %d bytes "
                                    "(leaf tensors and tables alone need more)" % int(memory * 8))

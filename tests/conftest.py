@@ -13,6 +13,14 @@ GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # a hung GPU test must not eat the box's time budget: every test gets a timeout (pytest-timeout is in the image)
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(420))
 
 
 def golden_names():

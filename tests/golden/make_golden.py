@@ -4,9 +4,9 @@
 Runs only in the build container (needs /root/reference).  Nothing here is used at test
 time: the tests read the committed outputs.  What it does:
 
-1. copies /root/reference/{src,solvers/flow-cutter-pace17,benchmarks} to a scratch directory
-   (the mount is read-only), builds the five Cython extensions with the reference's own
-   `setup.py build_ext --inplace` and FlowCutter with g++ (SURVEY.md Appendix A);
+1. builds the reference into the git-ignored oracle/_ref/ (oracle/reference.py: the five Cython
+   extensions with the reference's own `setup.py build_ext --inplace`, FlowCutter with g++,
+   SURVEY.md Appendix A);
 2. (re)generates the cubic vertex-cover CNF family the reference ships one member of
    (`benchmarks/cubic_vertex_cover/cubic_vc_50_0.cnf`): networkx.random_regular_graph(3, n, seed)
    -> one clause "u v 0" per edge;
@@ -34,42 +34,19 @@ import warnings
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 REF_SRC = "/root/reference"
-REF_BUILD = os.environ.get("TENSORORDER_REF_BUILD", "/tmp/ref_probe")
 sys.path.insert(0, REPO)
 
 
 def ensure_reference_build():
-    marker = os.path.join(REF_BUILD, "solvers/flow-cutter-pace17/flow_cutter_pace17")
-    so_ok = any(f.endswith(".so") for f in os.listdir(os.path.join(REF_BUILD, "src/tensor_network"))) \
-        if os.path.isdir(os.path.join(REF_BUILD, "src/tensor_network")) else False
-    if os.path.exists(marker) and so_ok:
-        return
-    os.makedirs(REF_BUILD, exist_ok=True)
-    for sub in ("src", "solvers/flow-cutter-pace17", "benchmarks"):
-        dst = os.path.join(REF_BUILD, sub)
-        if not os.path.exists(dst):
-            shutil.copytree(os.path.join(REF_SRC, sub), dst)
-    subprocess.check_call("chmod -R u+w " + REF_BUILD, shell=True)
-    subprocess.check_call([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=os.path.join(REF_BUILD, "src"))
-    subprocess.check_call(
-        "g++ -w -include string -std=c++11 -O3 -DNDEBUG src/*.cpp -o flow_cutter_pace17",
-        shell=True, cwd=os.path.join(REF_BUILD, "solvers/flow-cutter-pace17"))
+    """The reference is built once into the git-ignored oracle/_ref/ (oracle/reference.py)."""
+    from oracle import reference
+    if not reference.build():
+        raise RuntimeError("the reference could not be built into " + reference.REF_DIR)
 
 
 def import_reference():
-    warnings.filterwarnings("ignore")
-    import numpy
-    numpy.object = object  # numpy_apis.py:21 touches the removed alias on every entry_type call
-    sys.path.insert(0, os.path.join(REF_BUILD, "src"))
-    os.chdir(REF_BUILD)  # util.FileLocator resolves solvers/... relative to cwd (util.py:280-296)
-    sys.setrecursionlimit(100000)
-    import tensor_network, contraction_methods, planning, util  # noqa
-    from tensor_network import sliced_execution_plan
-    from util import boolean_formula
-    util.set_verbosity(0)
-    return dict(tensor_network=tensor_network, contraction_methods=contraction_methods, planning=planning,
-                util=util, sliced_execution_plan=sliced_execution_plan,
-                WeightFormat=boolean_formula.WeightFormat)
+    from oracle import reference
+    return reference.import_reference(chdir=True)  # the planners resolve solvers/... relative to the cwd
 
 
 # --------------------------------------------------------------------------------------

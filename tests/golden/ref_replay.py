@@ -19,39 +19,7 @@ sys.path.insert(0, HERE)
 import make_golden as mg  # noqa: E402
 
 
-def to_reference_plan(R, pp, as_int=False):
-    import numpy as np
-    from contraction_methods.contraction_tree import ContractionTreeContext
-    from tensor_network.tensor import BuiltTensor
-    from tensor_network.tensor_network import TensorNetwork
-
-    net = TensorNetwork()
-    slots = []
-    for t in pp.tensors:
-        arr = np.array(t["data"], dtype=np.float64).reshape(t["shape"])
-        if as_int:  # exact replays: Python ints in an object array, like the reference's own bigint leaves
-            assert np.array_equal(arr, np.rint(arr))
-            arr = np.array([int(x) for x in arr.reshape(-1)], dtype=object).reshape(t["shape"])
-        slots.append(net.add_node(BuiltTensor(arr)))
-    for e, (t1, t2) in enumerate(pp.edges):
-        a1 = pp.index_lists[t1].index(e)
-        a2 = pp.index_lists[t2].index(e)
-        got = net.connect(t1, a1, t2, a2)
-        assert got == e
-    for t, il in enumerate(pp.index_lists):
-        assert list(net.index_list(t)) == il
-    ctx = ContractionTreeContext()
-    ids = []
-    for node in pp.postorder:
-        if len(node) == 1:
-            ids.append(ctx.leaf(net, node[0]))
-        else:
-            ids.append(ctx.join(ids[node[0]], ids[node[1]]))
-    tree = ctx.get_tree(ids[-1])
-    plan = R["sliced_execution_plan"].SlicedExecutionPlan(tree, net)
-    plan.groups_to_slice = [set(g) for g in pp.groups_to_slice]
-    plan.edges_to_slice = set().union(*plan.groups_to_slice) if plan.groups_to_slice else set()
-    return plan
+from oracle.reference import to_reference_plan  # noqa: E402,F401  (kept importable from here)
 
 
 def main():

@@ -152,3 +152,45 @@ def run_program(desc, flat, first=0, count=None, stride=1, modulus=0, dag_seed=N
         run_list(desc["slice_ops"])
         sid += stride
     return acc
+
+
+def install_fake_device(compiled_plan_cls, setattr_fn=setattr, record=None):
+    """CPU tests of the host logic: replaces the device stage of `CompiledPlan` (leaf upload, modulus, run)
+    by this interpreter of the compiled program.  `record` (a dict) receives the slice range each run was given."""
+    import dataclasses
+
+    import numpy as np
+
+    state = {}
+
+    def fake_update_leaves(self, leaf_data=None):
+        if leaf_data is not None:
+            self.flat = dataclasses.replace(self.flat, leaf_data=np.ascontiguousarray(leaf_data, dtype=np.float64))
+        self.uploaded = True
+
+    def fake_upload(self):
+        self.uploaded = True
+
+    def fake_release(self):
+        self.uploaded = False
+
+    def fake_set_modulus(self, modulus):
+        state["modulus"] = int(modulus)
+
+    def fake_run(self, first=0, count=None, stride=1, initial=0.0, skip_invariant=False):
+        if record is not None:
+            a = record.setdefault("args", [first, 0, stride])
+            a[1] += count
+        m = state.get("modulus", 0)
+        r = run_program(self.describe(), self.flat, first=first, count=count, stride=stride, modulus=m) if count else 0.0
+        return (initial + r) % m if m else initial + r
+
+    setattr_fn(compiled_plan_cls, "update_leaves", fake_update_leaves)
+    setattr_fn(compiled_plan_cls, "upload", fake_upload)
+    setattr_fn(compiled_plan_cls, "release_device", fake_release)
+    setattr_fn(compiled_plan_cls, "set_modulus", fake_set_modulus)
+    setattr_fn(compiled_plan_cls, "run", fake_run)
+    setattr_fn(compiled_plan_cls, "last_ms", 0.0)
+    setattr_fn(compiled_plan_cls, "last_launches", 0)
+    setattr_fn(compiled_plan_cls, "last_gemm", (0.0, 0.0, 0))
+    return state

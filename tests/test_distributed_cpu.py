@@ -21,25 +21,13 @@ def _worker(rank, world, port, name, variant, limit, out):
     import torch.distributed as dist
 
     from conftest import load_golden
-    from program_sim import run_program
     from tensororder_b200 import api as api_mod
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     calls = {}
+    from program_sim import install_fake_device
 
-    def fake_upload(self):
-        self.uploaded = True
-
-    def fake_run(self, first=0, count=None, stride=1, initial=0.0, skip_invariant=False):
-        # the interruptible loop issues chunks; record the whole range this rank was given
-        a = calls.setdefault("args", [first, 0, stride])
-        a[1] += count
-        return initial + (run_program(self.describe(), self.flat, first=first, count=count, stride=stride) if count else 0.0)
-
-    api_mod.CompiledPlan.upload = fake_upload
-    api_mod.CompiledPlan.run = fake_run
-    api_mod.CompiledPlan.last_ms = 0.0
-    api_mod.CompiledPlan.last_launches = 0
+    install_fake_device(api_mod.CompiledPlan, record=calls)
     pp = load_golden(name).variant(variant)
     api = api_mod.B200API()
     api.add_argument("entry_type", "float64")
@@ -70,3 +58,62 @@ def test_two_ranks_partition_and_allreduce(name, variant, limit):
         assert count == (0 if rank >= total else (total - rank + 1) // 2)
         if count:
             assert first == rank
+
+
+def _failing_worker(rank, world, port, kind, out):
+    """Rank 1's device stage fails (OOM / timeout / other); rank 0's works.  Both must raise the same class
+    instead of rank 0 blocking in the all-reduce or summing partials of different slicings."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    from conftest import load_golden
+    from program_sim import install_fake_device
+    from tensororder_b200 import api as api_mod
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    install_fake_device(api_mod.CompiledPlan)
+    if rank == 1:
+        exc = {"oom": api_mod.OutOfMemoryError("arena does not fit"), "timeout": TimeoutError("alarm"),
+               "other": RuntimeError("CUDA error")}[kind]
+
+        def failing_update(self, leaf_data=None):
+            raise exc
+
+        api_mod.CompiledPlan.update_leaves = failing_update
+    pp = load_golden("vc50_lineflow").variant("min3")
+    plan = pp.as_execution_plan()
+    for entry_type in ("float64", "bigint"):
+        api = api_mod.B200API()
+        api.add_argument("entry_type", entry_type)
+        try:
+            api.contract_sliced(plan)
+            out[(rank, entry_type)] = "no error"
+        except api_mod.OutOfMemoryError:
+            out[(rank, entry_type)] = "oom"
+        except TimeoutError:
+            out[(rank, entry_type)] = "timeout"
+        except RuntimeError:
+            out[(rank, entry_type)] = "other"
+    # the ranks are still in step: a healthy collective call afterwards succeeds on both
+    if rank == 1:
+        install_fake_device(api_mod.CompiledPlan)
+    api = api_mod.B200API()
+    api.add_argument("entry_type", "float64")
+    out[(rank, "after")] = float(api.contract_sliced(plan))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["oom", "timeout", "other"])
+def test_a_failure_on_one_rank_is_raised_on_every_rank(kind):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29850 + (os.getpid() % 100)
+    mp.spawn(_failing_worker, args=(2, port, kind, out), nprocs=2, join=True)
+    for rank in range(2):
+        for entry_type in ("float64", "bigint"):
+            assert out[(rank, entry_type)] == kind, (rank, entry_type, dict(out))
+        assert out[(rank, "after")] == 2802717837.0

@@ -27,24 +27,10 @@ def test_primes_and_crt():
 
 def _fake_device(monkeypatch):
     """Replace the device stage by the numpy interpreter of the compiled program (CPU test of the host logic)."""
-    state = {}
+    from program_sim import install_fake_device
 
-    def fake_upload(self):
-        self.uploaded = True
-
-    def fake_set_modulus(self, modulus):
-        state["modulus"] = int(modulus)
-
-    def fake_run(self, first=0, count=None, stride=1, initial=0.0, skip_invariant=False):
-        m = state.get("modulus", 0)
-        r = run_program(self.describe(), self.flat, first=first, count=count, stride=stride, modulus=m) if count else 0.0
-        return (initial + r) % m if m else initial + r
-
-    monkeypatch.setattr(api_mod.CompiledPlan, "upload", fake_upload)
-    monkeypatch.setattr(api_mod.CompiledPlan, "set_modulus", fake_set_modulus)
-    monkeypatch.setattr(api_mod.CompiledPlan, "run", fake_run)
-    monkeypatch.setattr(api_mod.CompiledPlan, "last_ms", 0.0)
-    monkeypatch.setattr(api_mod.CompiledPlan, "last_launches", 0)
+    api_mod.PLAN_CACHE.clear()
+    return install_fake_device(api_mod.CompiledPlan, monkeypatch.setattr)
 
 
 @pytest.mark.parametrize("name", [n for n in EXACT if load_golden(n).expected["maxrank"] <= 15])

@@ -1,33 +1,68 @@
-"""Drop-in check against the REAL reference (build container only: needs /root/reference; skipped on the
-GPU box).  Registers "b200" in the reference's live registry, resolves it through the reference's own
-click option type, and drives `execution.run` with a reference-built plan up to the C ABI.  Without a
-GPU the backend must fail loudly (no CPU fallback) and the reference must report it the way it reports
-any backend failure (execution.py:143-152)."""
-import io
+"""Drop-in checks against the REAL reference, built into the git-ignored oracle/_ref/ (oracle/reference.py),
+which travels to the GPU box.  Registers "b200" in the reference's live registry, resolves it through the
+reference's own click option type, and drives `execution.run` and both unmodified CLIs
+(`src/execution.py`, `src/tensororder.py`) with the backend.
+
+Without a GPU (`-m "not gpu"`) the backend must fail loudly (no CPU fallback) and the reference must
+report it the way it reports any backend failure (execution.py:143-152); with one (`-m gpu`) the counts
+must equal the reference's own numpy run of the same plan and `Contraction Time:` must be reported."""
 import os
+import re
 import subprocess
 import sys
 
 import pytest
 
-REF = "/root/reference"
-BUILD = os.environ.get("TENSORORDER_REF_BUILD", "/tmp/ref_probe")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from oracle import reference  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+pytestmark = pytest.mark.skipif(not reference.available(), reason="oracle/_ref is not built (needs /root/reference once)")
+REF_DIR = reference.REF_DIR
 
 
 @pytest.fixture(scope="module")
 def ref():
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import make_golden as mg
-
-    cwd = os.getcwd()
-    mg.ensure_reference_build()
-    R = mg.import_reference()
-    yield R
-    os.chdir(cwd)
+    return reference.import_reference()
 
 
+def _has_gpu():
+    from tensororder_b200 import cabi
+
+    return cabi.lib.tob_device_count() > 0
+
+
+def _cli(script, args, stdin_bytes, library="b200", timeout=600, torchrun=0):
+    """Runs an unmodified reference CLI through the launcher, from oracle/_ref (the planners resolve
+    `solvers/...` relative to the cwd); returns (stdout, stderr)."""
+    env = dict(os.environ, PYTHONPATH=REPO)
+    cmd = [sys.executable]
+    if torchrun:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(torchrun),
+                "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300)]
+    cmd += ["-m", "tensororder_b200.launch", os.path.join(REF_DIR, "src", script), "--tensor_library=" + library] + args
+    res = subprocess.run(cmd, input=stdin_bytes, capture_output=True, env=env, cwd=REF_DIR, timeout=timeout)
+    return res.stdout.decode(), res.stderr.decode(), res.returncode
+
+
+def _field(out, key):
+    m = re.search(r"^%s: (.*)$" % re.escape(key), out, re.M)
+    return m.group(1).strip() if m else None
+
+
+def _con_bytes(ref, name, tmp_path):
+    from conftest import load_golden
+
+    path = str(tmp_path / (name.replace(":", "_") + ".con"))
+    base, _, variant = name.partition(":")
+    pp = load_golden(base)
+    reference.write_con(ref, pp.variant(variant) if variant else pp, path)
+    return open(path, "rb").read()
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side (CPU) checks
+# ---------------------------------------------------------------------------------------------------
 def test_registration_and_option_resolution(ref):
     from tensororder_b200.api import B200API, register
 
@@ -43,37 +78,33 @@ def test_flatten_reads_reference_objects_like_stored_plans(ref):
     copy of the same plan (the golden fixture was exported from such objects)."""
     import numpy as np
 
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import ref_replay
     from conftest import load_golden
-    from tensororder_b200.flatten import flatten_plan
+    from tensororder_b200.flatten import flatten_plan, rebuild_leaf_data
 
     pp = load_golden("vc50_lineflow").variant("min3")
-    live = ref_replay.to_reference_plan(ref, pp)
+    live = reference.to_reference_plan(ref, pp)
     a = flatten_plan(live)
     b = flatten_plan(pp.as_execution_plan())
     for f in ("node_left", "node_right", "node_leaf", "leaf_rank", "leaf_data_offset", "leaf_axis_start",
               "leaf_axis_edge", "leaf_data"):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
     assert a.n_slice_groups == b.n_slice_groups == 3
+    assert np.array_equal(rebuild_leaf_data(live, a), a.leaf_data)  # what a plan-cache hit re-reads
 
 
 def test_execution_run_reaches_the_cabi(ref, capsys):
     import execution  # the reference's src/execution.py
     import tensor_network
 
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import ref_replay
     from conftest import load_golden
-    from tensororder_b200 import cabi
     from tensororder_b200.api import B200API
 
-    plan = ref_replay.to_reference_plan(ref, load_golden("vc50_lineflow"))
+    plan = reference.to_reference_plan(ref, load_golden("vc50_lineflow"))
     api = B200API()
     api.add_argument("entry_type", "float64")
     ref["util"].set_verbosity(0)
     result = execution.run(plan, api, tensor_network.ALL_SLICERS["greedy_mem"], None)
-    if cabi.lib.tob_device_count() > 0:
+    if _has_gpu():
         assert float(result) == 2802717837.0
     else:
         # no GPU here: the backend raises, the reference prints its generic backend-failure line
@@ -84,26 +115,27 @@ def test_execution_run_reaches_the_cabi(ref, capsys):
 
 
 def test_launcher_runs_the_unmodified_cli_help():
-    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    res = subprocess.run([sys.executable, "-m", "tensororder_b200.launch", os.path.join(BUILD, "src", "execution.py"), "--help"],
-                         capture_output=True, text=True, env=env, cwd=BUILD)
-    assert res.returncode == 0, res.stderr
-    assert "b200" in res.stdout  # listed among the --tensor_library choices
+    out, err, rc = _cli("execution.py", ["--help"], b"")
+    assert rc == 0, err
+    assert "b200" in out  # listed among the --tensor_library choices
+    assert "b200_mem" in out  # and the GPU-aware slicer among --slicer
+
+
+def test_launcher_reference_numpy_through_con_file(ref, tmp_path):
+    """The `.con` files the tests hand to `execution.py` are what `planning.py --store` writes: the
+    reference's own numpy backend reads one and reproduces the stored count."""
+    out, err, rc = _cli("execution.py", [], _con_bytes(ref, "vc50_lineflow", tmp_path), library="numpy")
+    assert rc == 0, err
+    assert float(_field(out, "Count")) == 2802717837.0
+    assert float(_field(out, "Contraction Time")) > 0
 
 
 def test_gpu_aware_slicer_slices_less_than_the_reference_model(ref):
     """Same plan, same byte budget: the reference cost model (out + 2*left + 2*right entries) needs more
-    slices than the executor's real arena; the count is unchanged (interpreted from the compiled program)."""
-    import math
-
+    slices than the executor's real arena."""
     import tensor_network
 
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import ref_replay
     from conftest import load_golden
-    from program_sim import run_program
-    from tensororder_b200.api import CompiledPlan
-    from tensororder_b200.flatten import flatten_plan
     from tensororder_b200.slicer import B200MemSlicer, plan_peak_bytes, register
 
     register()
@@ -111,20 +143,164 @@ def test_gpu_aware_slicer_slices_less_than_the_reference_model(ref):
     pp = load_golden("vc250_lineflow")
     assert pp.expected["maxrank"] == 31
     budget_bytes = 40e9  # between the executor's real need (30.6 GB) and the reference model's estimate (55.8 GB)
-    ref_plan = ref_replay.to_reference_plan(ref, pp)
+    ref_plan = reference.to_reference_plan(ref, pp)
     assert ref_plan.memory * 8 > budget_bytes
     tensor_network.ALL_SLICERS["greedy_mem"].slice_until(ref_plan, memory=budget_bytes / 8)
-    ours = ref_replay.to_reference_plan(ref, pp)
+    ours = reference.to_reference_plan(ref, pp)
     B200MemSlicer().slice_until(ours, memory=budget_bytes / 8)
     assert plan_peak_bytes(ours) <= budget_bytes
     assert len(ours.groups_to_slice) == 0 < len(ref_plan.groups_to_slice)
     # a budget that needs real slicing: still met, with at most as many slices as the reference model asks for
     tight = 8e9
-    a = ref_replay.to_reference_plan(ref, pp)
+    a = reference.to_reference_plan(ref, pp)
     tensor_network.ALL_SLICERS["greedy_mem"].slice_until(a, memory=tight / 8)
-    b = ref_replay.to_reference_plan(ref, pp)
+    b = reference.to_reference_plan(ref, pp)
     B200MemSlicer().slice_until(b, memory=tight / 8)
     assert plan_peak_bytes(b) <= tight and 0 < len(b.groups_to_slice) <= len(a.groups_to_slice)
     pp = load_golden("vc100_lineflow")
     with pytest.raises(RuntimeError):
-        B200MemSlicer().slice_until(ref_replay.to_reference_plan(ref, pp), memory=16)  # 128 bytes: impossible
+        B200MemSlicer().slice_until(reference.to_reference_plan(ref, pp), memory=16)  # 128 bytes: impossible
+
+
+def test_launcher_under_torchrun_shares_stdin_and_plan(ref, tmp_path):
+    """torchrun's workers inherit ONE stdin and the planners are timing-dependent: the launcher reads stdin
+    on rank 0 only and broadcasts it, and plans on rank 0 only.  Two gloo ranks, reference numpy
+    backend (no GPU needed): both CLIs must finish and rank 0 must report the right count."""
+    out, err, rc = _cli("execution.py", [], _con_bytes(ref, "vc50_lineflow:min3", tmp_path), library="numpy", torchrun=2)
+    assert rc == 0, err[-2000:]
+    assert out.count("Count:") == 1 and float(_field(out, "Count")) == 2802717837.0
+    cnf = open(os.path.join(REF_DIR, "benchmarks", "cubic_vertex_cover", "cubic_vc_50_0.cnf"), "rb").read()
+    out, err, rc = _cli("tensororder.py", ["--planner=line-Flow", "--weights=unweighted", "--seed=1", "--timeout=30"], cnf,
+                        library="numpy", torchrun=2)
+    assert rc == 0, err[-2000:]
+    assert out.count("Count:") == 1 and float(_field(out, "Count")) == 2802717837.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# the real reference -> b200 -> count path on the device
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_execution_run_with_reference_objects(ref):
+    """`execution.run(plan, B200API, slicer, cutoff)` (src/execution.py:122-152) on live reference objects:
+    unsliced, sliced, slice_cutoff; counts equal the reference's numpy backend on the same plan objects."""
+    import execution
+    import tensor_network
+
+    from conftest import load_golden
+    from tensororder_b200.api import B200API
+
+    numpy_api = tensor_network.ALL_APIS["numpy"]()
+    numpy_api.add_argument("entry_type", "float64")
+    slicer = tensor_network.ALL_SLICERS["greedy_mem"]
+    for name, variant, cutoff in (("vc50_lineflow", None, None), ("vc50_lineflow", "min3", None),
+                                  ("vc50_lineflow", "min3", 3), ("vc100_lineflow", "min4", None),
+                                  ("vc50_mcc_factorflow", "min3", None)):
+        pp = load_golden(name)
+        pp = pp.variant(variant) if variant else pp
+        plan = reference.to_reference_plan(ref, pp)
+        api = B200API()
+        api.add_argument("entry_type", "float64")
+        got = execution.run(plan, api, slicer, cutoff)
+        want = execution.run(plan, numpy_api, slicer, cutoff)
+        assert got is not None and want is not None
+        assert abs(float(got) - float(want)) <= 1e-9 * abs(float(want)), (name, variant, cutoff)
+        if name == "vc50_lineflow" and cutoff is None:
+            assert float(got) == float(want) == 2802717837.0  # representable: bit-exact
+
+
+@pytest.mark.gpu
+def test_gpu_oom_retry_loop_slices_until_the_plan_fits(ref):
+    """The reference's recovery path (execution.py:133-142): the backend raises the reference's OWN
+    OutOfMemoryError class, `run` slices once more and retries; the count is unchanged."""
+    import execution
+    import tensor_network
+
+    from conftest import load_golden
+    from tensororder_b200.api import B200API
+
+    plan = reference.to_reference_plan(ref, load_golden("vc150_lineflow"))
+    api = B200API()
+    api.add_argument("entry_type", "float64")
+    api.add_argument("mem_limit_bytes", 30000000)  # the unsliced arena needs 55 MB: forces re-slicing (4 groups)
+    got = execution.run(plan, api, tensor_network.ALL_SLICERS["greedy_mem"], None)
+    assert 1 <= len(plan.groups_to_slice) <= 8
+    assert api.last_stats["peak_bytes"] <= 30000000
+    want = load_golden("vc150_lineflow").expected["count"]
+    assert abs(float(got) - want) <= 1e-9 * want
+    # a limit no slicing can meet ends the reference's retry loop with its out-of-memory line instead of spinning
+    plan = reference.to_reference_plan(ref, load_golden("vc50_lineflow"))
+    api = B200API()
+    api.add_argument("entry_type", "float64")
+    api.add_argument("mem_limit_bytes", 1000)
+    assert execution.run(plan, api, tensor_network.ALL_SLICERS["greedy_mem"], None) is None
+
+
+@pytest.mark.gpu
+def test_gpu_cli_execution_py_count_and_contraction_time(ref, tmp_path):
+    """`python -m tensororder_b200.launch src/execution.py --tensor_library=b200 < N.con`: the line the
+    metric is read from (`Contraction Time:`, src/util/util.py:166-174) and `Count:` next to the numpy run of
+    the same `.con`."""
+    for name in ("vc50_lineflow", "vc150_lineflow", "vc150_mcc_factorflow"):
+        con = _con_bytes(ref, name, tmp_path)
+        out_b, err_b, rc_b = _cli("execution.py", [], con, library="b200")
+        out_n, err_n, rc_n = _cli("execution.py", [], con, library="numpy")
+        assert rc_b == 0 and rc_n == 0, (err_b[-1500:], err_n[-1500:])
+        cb, cn = float(_field(out_b, "Count")), float(_field(out_n, "Count"))
+        assert abs(cb - cn) <= 1e-9 * abs(cn), (name, cb, cn)
+        tb, tn = float(_field(out_b, "Contraction Time")), float(_field(out_n, "Contraction Time"))
+        assert tb > 0 and tn > 0
+        print("%s: Count %r | Contraction Time b200 %.4f s (first call: CUDA context + plan compile), numpy %.4f s"
+              % (name, cb, tb, tn))
+    # rank / memory limits and the slicers go through the reference's own option handling
+    con = _con_bytes(ref, "vc100_lineflow", tmp_path)
+    want = float(_field(_cli("execution.py", [], con, library="numpy")[0], "Count"))
+    for args in (["--rank_limit=10"], ["--mem_limit=100000", "--slicer=b200_mem"], ["--rank_limit=12", "--slice_cutoff=2"]):
+        out_b, err_b, rc = _cli("execution.py", args, con, library="b200")
+        assert rc == 0, err_b[-1500:]
+        out_n, _, _ = _cli("execution.py", [a for a in args if "b200_mem" not in a], con, library="numpy")
+        if "--slice_cutoff=2" in args:
+            assert abs(float(_field(out_b, "Count")) - float(_field(out_n, "Count"))) <= 1e-9 * abs(float(_field(out_n, "Count")))
+        else:
+            assert abs(float(_field(out_b, "Count")) - want) <= 1e-9 * want, args
+        assert int(_field(out_b, "# Network Slices")) >= 2
+
+
+@pytest.mark.gpu
+def test_gpu_cli_tensororder_py_end_to_end():
+    """The README command (README.md:21) with `--tensor_library=b200`: reduction, planning (FlowCutter
+    subprocess), slicing, `--early` and execution all inside the unmodified `src/tensororder.py`."""
+    cnf = open(os.path.join(REF_DIR, "benchmarks", "cubic_vertex_cover", "cubic_vc_50_0.cnf"), "rb").read()
+    base = ["--planner=line-Flow", "--weights=unweighted", "--seed=1", "--timeout=60", "--verbosity=2"]
+    for extra in ([], ["--minimum_slice=3"], ["--early=6"], ["--early=6", "--minimum_slice=2"], ["--entry_type=bigint"],
+                  ["--entry_type=int"], ["--entry_type=float32"], ["--planner=factor-Flow", "--slicer=b200_mem"]):
+        out, err, rc = _cli("tensororder.py", base + extra, cnf, library="b200")
+        assert rc == 0, err[-1500:]
+        count = _field(out, "Count")
+        assert count is not None, (extra, out[-800:], err[-800:])
+        assert float(count) == pytest.approx(2802717837.0, rel=(1e-6 if "--entry_type=float32" in extra else 0)), (extra, count)
+        assert float(_field(out, "Contraction Time")) > 0
+
+
+@pytest.mark.gpu
+def test_gpu_b200_mem_slicer_contracts_within_the_budget(ref):
+    """slice with `B200MemSlicer` until the EXECUTOR's arena fits the byte budget, contract
+    on the device, same count as unsliced and `peak_bytes <= budget` (cf. GreedyMemSlicer, slicers.py:27-33)."""
+    from conftest import load_golden
+    from tensororder_b200.api import B200API, CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+    from tensororder_b200.slicer import B200MemSlicer
+
+    for name, budget in (("vc150_lineflow", 2.5e7), ("vc200_lineflow", 5e8)):
+        pp = load_golden(name)
+        want = pp.expected["count"]
+        plan = reference.to_reference_plan(ref, pp)
+        unsliced_peak = CompiledPlan(flatten_plan(plan)).peak_bytes  # host-only compile
+        assert unsliced_peak > budget
+        B200MemSlicer().slice_until(plan, memory=budget / 8)
+        assert len(plan.groups_to_slice) >= 1
+        api = B200API()
+        api.add_argument("entry_type", "float64")
+        api.add_argument("mem_limit_bytes", int(budget))
+        got = float(api.contract_sliced(plan))
+        assert api.last_stats["peak_bytes"] <= budget
+        assert abs(got - want) <= 1e-9 * want, (name, got, want)

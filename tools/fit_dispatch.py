@@ -1,0 +1,271 @@
+"""Generates tensororder_b200/csrc/tob_dispatch_table.h from measurements on the GPU (north_star: "the choice
+per node made from measured counters").  Runs single joins through `tob_tensordot_device` (GEMM-ready operands)
+under `tob_tuning_set` overrides and derives
+
+  A. the split-K time model's constants (alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us): every power-of-two
+     split of a grid of GEMM shapes is timed, the constants are fitted to the measured times (least squares on
+     log(model / measured)), and the table prints the split the fitted model picks next to the measured best;
+  B. the generic <-> DMMA GEMM crossover (gemm_min_total for k >= 4, gemm_smallk_min_out for 1 <= k <= 3);
+  C. the generic kernel classes (t1_max_k, t32_max_k) and the persistent short-K range (persist_max_k).
+
+Usage (GPU box):  python tools/fit_dispatch.py [--quick]
+Writes gpurun_out/dispatch_fit.json (raw measurements) and gpurun_out/tob_dispatch_table.h (copy it over
+tensororder_b200/csrc/tob_dispatch_table.h and rebuild)."""
+import ctypes
+import datetime
+import itertools
+import json
+import math
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tensororder_b200 import cabi  # noqa: E402
+
+lib = cabi.lib
+P32 = ctypes.POINTER(ctypes.c_int32)
+quick = "--quick" in sys.argv
+DEFAULTS = {}
+
+
+def tset(key, value):
+    assert lib.tob_tuning_set(key.encode(), float(value)) == 0, cabi.last_error()
+
+
+def tget(key):
+    v = ctypes.c_double()
+    assert lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0, cabi.last_error()
+    return v.value
+
+
+KEYS = ["gemm_min_free", "gemm_min_k", "gemm_min_total", "gemm_smallk_min_free", "gemm_smallk_min_out", "t1_max_k",
+        "t32_max_k", "t32_min_out", "persist_max_k", "sm_gflops", "alone_frac", "gemm_fix_us", "reduce_gbs",
+        "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2"]
+for k_ in KEYS:
+    DEFAULTS[k_] = tget(k_)
+
+
+def restore():
+    for k_, v in DEFAULTS.items():
+        tset(k_, v)
+
+
+_bufs = {}
+
+
+def buf(n_doubles, tag):
+    key = (tag, n_doubles)
+    if key not in _bufs:
+        for old in [k2 for k2 in _bufs if k2[0] == tag]:
+            del _bufs[old]
+        torch.cuda.empty_cache()
+        _bufs[key] = torch.rand(n_doubles, dtype=torch.float64, device="cuda")
+    return _bufs[key]
+
+
+def time_join(m, n, k, policy=0, reps=5, ws_log2=None):
+    """Best-of-reps contraction time (us) and the kernel kind of C[2^(m+n)] = A[2^(m+k)] . B[2^(n+k)]."""
+    ra, rb, rc = m + k, n + k, m + n
+    a, b, c = buf(1 << ra, "a"), buf(1 << rb, "b"), buf(1 << rc, "c")
+    ws_n = 1 << (ws_log2 if ws_log2 is not None else min(rc + 8, 28))
+    ws = buf(ws_n + 512, "ws")
+    aa = np.arange(ra - k, ra, dtype=np.int32)
+    ab = np.arange(rb - k, rb, dtype=np.int32)
+    best, kind = None, None
+    for rep in range(reps + 1):
+        ms = (ctypes.c_float * 3)()
+        torch.cuda.synchronize()
+        rc_ = lib.tob_tensordot_device(a.data_ptr(), ra, b.data_ptr(), rb, aa.ctypes.data_as(P32), ab.ctypes.data_as(P32), k,
+                                       c.data_ptr(), ws.data_ptr(), 8 * ws_n, policy, None, ms)
+        assert rc_ == 0, cabi.last_error()
+        if rep and (best is None or ms[1] < best):
+            best = ms[1]
+        kind = int(ms[2])
+    return best * 1e3, kind
+
+
+def model_us(m, n, k, c):
+    lib.tob_gemm_time_model_us.restype = ctypes.c_double
+    lib.tob_gemm_time_model_us.argtypes = [ctypes.c_int32] * 6
+    return lib.tob_gemm_time_model_us(m, n, k, min(m, 7), min(n, 6), c)
+
+
+out = {"when": datetime.datetime.utcnow().isoformat() + "Z", "gpu": torch.cuda.get_device_name(0)}
+
+# ---------------------------------------------------------------------------------------------------
+# A. split-K
+# ---------------------------------------------------------------------------------------------------
+shapes = []
+for T in ([28, 32] if quick else [26, 28, 30, 32, 34]):
+    for k in ([8, 12, 16] if quick else [8, 10, 12, 14, 16]):
+        m = (T - k + 1) // 2
+        n = T - k - m
+        if n >= 6:
+            shapes.append((m, n, k))
+shapes += [(11, 10, 10), (11, 10, 9), (10, 10, 9), (12, 11, 12), (14, 13, 10)]
+rows = []
+for (m, n, k) in shapes:
+    for c in range(0, 9):
+        if k - c < 6 or (m + n + c) > 28:
+            break
+        tset("force_ksplit_log2", c)
+        us, kind = time_join(m, n, k)
+        rows.append({"m": m, "n": n, "k": k, "c": c, "us": us, "kind": kind})
+restore()
+out["splitk"] = rows
+print("split-K calibration: %d timings" % len(rows))
+
+# fit: grid search, then report
+grid = {"alone_frac": [0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.9, 1.0], "gemm_fix_us": [2, 3, 4, 5, 6, 8, 10, 12],
+        "reduce_gbs": [1500, 2000, 2500, 3000, 3500, 4000, 4500, 5500], "reduce_fix_us": [1, 2, 3, 4, 6, 8]}
+best_fit = None
+for vals in itertools.product(*grid.values()):
+    for key, v in zip(grid.keys(), vals):
+        tset(key, v)
+    err = 0.0
+    for r in rows:
+        err += math.log(model_us(r["m"], r["n"], r["k"], r["c"]) / r["us"]) ** 2
+    if best_fit is None or err < best_fit[0]:
+        best_fit = (err, dict(zip(grid.keys(), vals)))
+restore()
+fit = best_fit[1]
+out["fit"] = {"rms_log_error": math.sqrt(best_fit[0] / len(rows)), **fit}
+print("fitted:", out["fit"])
+for key, v in fit.items():
+    tset(key, v)
+    DEFAULTS[key] = v
+print("| m | n | k | measured us by split c | measured best c | model picks c | loss vs best |")
+print("|---|---|---|---|---|---|---|")
+picks = []
+for (m, n, k) in shapes:
+    rs = [r for r in rows if (r["m"], r["n"], r["k"]) == (m, n, k)]
+    meas_best = min(rs, key=lambda r: r["us"])
+    pick, bt = 0, model_us(m, n, k, 0)
+    for r in rs[1:]:
+        t = model_us(m, n, k, r["c"])
+        if t < bt * 0.97:
+            pick, bt = r["c"], t
+    got = [r for r in rs if r["c"] == pick][0]["us"]
+    picks.append({"m": m, "n": n, "k": k, "best_c": meas_best["c"], "best_us": meas_best["us"], "model_c": pick, "model_c_us": got,
+                  "tflops_at_pick": 2.0 * 2.0 ** (m + n + k) / got / 1e6})
+    print("| %d | %d | %d | %s | %d (%.1f) | %d (%.1f) | %.1f%% |" % (
+        m, n, k, " ".join("%d:%.1f" % (r["c"], r["us"]) for r in rs), meas_best["c"], meas_best["us"], pick, got,
+        100 * (got / meas_best["us"] - 1)))
+out["splitk_picks"] = picks
+
+# ---------------------------------------------------------------------------------------------------
+# B. generic <-> GEMM crossover
+# ---------------------------------------------------------------------------------------------------
+cross = []
+tset("gemm_min_total", 0)
+tset("gemm_smallk_min_out", 0)
+tset("gemm_smallk_min_free", 7)
+for k in ([4, 6, 8] if quick else [4, 5, 6, 7, 8, 10]):
+    for tot in range(16, 25):
+        m = (tot - k + 1) // 2
+        n = tot - k - m
+        if n < 6:
+            continue
+        g, kind_g = time_join(m, n, k, policy=0)
+        s, _ = time_join(m, n, k, policy=1)
+        cross.append({"m": m, "n": n, "k": k, "total": tot, "gemm_us": g, "generic_us": s, "gemm_kind": kind_g})
+for k in (1, 2, 3):
+    for outs in range(14, 23, 2):
+        m = n = outs // 2
+        g, kind_g = time_join(m, n, k, policy=0)
+        s, _ = time_join(m, n, k, policy=1)
+        cross.append({"m": m, "n": n, "k": k, "outs": outs, "gemm_us": g, "generic_us": s, "gemm_kind": kind_g})
+restore()
+out["crossover"] = cross
+# smallest total from which the GEMM kernel wins for every k >= 4 row measured at that total and above
+tot_wins = {}
+for r in cross:
+    if "total" in r and r["gemm_kind"] == 1:
+        tot_wins.setdefault(r["total"], []).append(r["gemm_us"] <= r["generic_us"] * 1.02)
+gemm_min_total = int(DEFAULTS["gemm_min_total"])
+for tot in sorted(tot_wins, reverse=True):
+    if all(tot_wins[tot]):
+        gemm_min_total = tot
+    else:
+        break
+outs_wins = {}
+for r in cross:
+    if "outs" in r and r["gemm_kind"] == 1:
+        outs_wins.setdefault(r["outs"], []).append(r["gemm_us"] <= r["generic_us"] * 1.02)
+smallk_min_out = int(DEFAULTS["gemm_smallk_min_out"])
+for o in sorted(outs_wins, reverse=True):
+    if all(outs_wins[o]):
+        smallk_min_out = o
+    else:
+        break
+print("crossover: gemm_min_total ->", gemm_min_total, " gemm_smallk_min_out ->", smallk_min_out)
+for r in cross:
+    print("  m=%d n=%d k=%d  gemm %.1f us  generic %.1f us  (%s)" % (r["m"], r["n"], r["k"], r["gemm_us"], r["generic_us"],
+                                                                  "gemm kernel" if r["gemm_kind"] == 1 else "generic both"))
+
+# ---------------------------------------------------------------------------------------------------
+# C. generic classes and the persistent short-K range
+# ---------------------------------------------------------------------------------------------------
+classes = []
+for outs in (12, 16, 20):
+    for k in range(4, 13):
+        m = (outs + 1) // 2
+        n = outs - m
+        res = {}
+        for name, t1, t32 in (("t1", 99, 99), ("t32", -1, 99), ("t256", -1, -1)):
+            if name == "t1" and k > 6:
+                continue  # the one-thread kernel walks K <= 64 only
+            tset("t1_max_k", t1)
+            tset("t32_max_k", t32)
+            tset("t32_min_out", 0)
+            res[name], _ = time_join(m, n, k, policy=1)
+        restore()
+        classes.append({"outs": outs, "k": k, **res})
+        print("  generic classes outs=2^%d k=%d: %s" % (outs, k, {a: round(b, 1) for a, b in res.items()}))
+out["generic_classes"] = classes
+t1_max_k = max([r["k"] for r in classes if "t1" in r and r["t1"] <= min(r["t32"], r["t256"]) * 1.02] or [int(DEFAULTS["t1_max_k"])])
+t32_max_k = max([r["k"] for r in classes if r["outs"] >= 12 and r["t32"] <= r["t256"] * 1.02] or [int(DEFAULTS["t32_max_k"])])
+persist = []
+for k in range(1, 8):
+    m, n = (32 - k + 1) // 2, (32 - k) // 2
+    tset("persist_max_k", 99)
+    p_us, _ = time_join(m, n, k)
+    tset("persist_max_k", -1)
+    o_us, _ = time_join(m, n, k)
+    restore()
+    persist.append({"m": m, "n": n, "k": k, "persistent_us": p_us, "one_tile_per_cta_us": o_us})
+    print("  persistent short-K m=%d n=%d k=%d: %.1f vs %.1f us" % (m, n, k, p_us, o_us))
+out["persistent"] = persist
+persist_max_k = max([r["k"] for r in persist if r["persistent_us"] <= r["one_tile_per_cta_us"] * 1.01] or [int(DEFAULTS["persist_max_k"])])
+
+# ---------------------------------------------------------------------------------------------------
+table = {
+    "GEMM_MIN_FREE": int(DEFAULTS["gemm_min_free"]), "GEMM_MIN_K": int(DEFAULTS["gemm_min_k"]), "GEMM_MIN_TOTAL": gemm_min_total,
+    "GEMM_SMALLK_MIN_FREE": int(DEFAULTS["gemm_smallk_min_free"]), "GEMM_SMALLK_MIN_OUT": smallk_min_out,
+    "T1_MAX_K": min(t1_max_k, 6), "T32_MAX_K": t32_max_k, "T32_MIN_OUT": int(DEFAULTS["t32_min_out"]),
+    "PERSIST_MAX_K": persist_max_k, "SM_GFLOPS": DEFAULTS["sm_gflops"], "ALONE_FRAC": fit["alone_frac"],
+    "GEMM_FIX_US": float(fit["gemm_fix_us"]), "REDUCE_GBS": float(fit["reduce_gbs"]), "REDUCE_FIX_US": float(fit["reduce_fix_us"]),
+    "MAX_KSPLIT_LOG2": int(DEFAULTS["max_ksplit_log2"]), "MIN_K_PER_SPLIT_LOG2": int(DEFAULTS["min_k_per_split_log2"]),
+}
+out["table"] = table
+os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(REPO, "gpurun_out", "dispatch_fit.json"), "w"), indent=1)
+src = open(os.path.join(REPO, "tensororder_b200", "csrc", "tob_dispatch_table.h")).read().split("\n")
+lines = []
+for ln in src:
+    if ln.startswith("// generated:"):
+        ln = "// generated: %s on %s by tools/fit_dispatch.py (fit rms log error %.3f over %d timings; raw: profiles/r02_dispatch_fit.json)" % (
+            out["when"], out["gpu"], out["fit"]["rms_log_error"], len(rows))
+    if ln.startswith("#define TOB_TUNE_"):
+        name = ln.split()[1][len("TOB_TUNE_"):]
+        if name in table:
+            comment = ln[ln.index("//"):] if "//" in ln else ""
+            v = table[name]
+            ln = ("#define TOB_TUNE_%s %s" % (name, ("%d" % v) if isinstance(v, int) else ("%.4g" % v if v < 100 else "%.1f" % v))).ljust(42) + comment
+    lines.append(ln)
+open(os.path.join(REPO, "gpurun_out", "tob_dispatch_table.h"), "w").write("\n".join(lines))
+print("wrote gpurun_out/dispatch_fit.json and gpurun_out/tob_dispatch_table.h")
