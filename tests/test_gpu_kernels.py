@@ -17,7 +17,7 @@ def _tensordot_device(a, b, axes_a, axes_b, policy=0):
     tb = torch.from_numpy(b.reshape(-1).copy()).cuda()
     rank_c = a.ndim + b.ndim - 2 * len(axes_a)
     tc = torch.empty(1 << rank_c, dtype=torch.float64, device="cuda")
-    ws_bytes = 8 * (a.size + b.size + (tc.numel() << 4)) + 1024
+    ws_bytes = 8 * (a.size + b.size + max(tc.numel() << 4, min(tc.numel() << 8, 1 << 27))) + 1024
     ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device="cuda")
     aa = np.asarray(axes_a, dtype=np.int32)
     ab = np.asarray(axes_b, dtype=np.int32)
@@ -110,3 +110,80 @@ def test_permute_matches_numpy_transpose(rank):
         torch.cuda.synchronize()
         want = np.transpose(x, perm) if rank else x
         assert np.array_equal(tout.cpu().numpy().reshape(want.shape), want)
+
+
+@pytest.fixture
+def tuning():
+    """Overrides single dispatch parameters (tob_tuning_set) for one test and restores the measured table afterwards."""
+    import ctypes
+
+    from tensororder_b200 import cabi
+
+    saved = {}
+
+    def set_(key, value):
+        if key not in saved:
+            v = ctypes.c_double()
+            assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0, cabi.last_error()
+            saved[key] = v.value
+        assert cabi.lib.tob_tuning_set(key.encode(), float(value)) == 0, cabi.last_error()
+
+    yield set_
+    for key, value in saved.items():
+        cabi.lib.tob_tuning_set(key.encode(), value)
+
+
+VARIANT_CASES = [
+    # long-K joins (K >= 256 per split): the warp-specialised kernel, LDGSTS feed vs 2-D tensor-map (TMA) feed
+    ({"gemm_feed": 0}, (18, 16, 9)), ({"gemm_feed": 1}, (18, 16, 9)), ({"gemm_feed": 1}, (21, 18, 9)),
+    ({"gemm_feed": 1}, (22, 22, 16)), ({"gemm_feed": 1}, (17, 17, 10)), ({"gemm_feed": 1, "force_ksplit_log2": 2}, (19, 18, 11)),
+    ({"gemm_feed": 1}, (16, 21, 10)),  # swapped operands (n > m)
+    # short-K persistent kernel: direct vs shared-memory-staged epilogue, every LOW-bit pattern of the output interleave
+    ({"persist_staged": 0}, (16, 14, 4)), ({"persist_staged": 1}, (16, 14, 4)), ({"persist_staged": 1}, (15, 13, 2)),
+    ({"persist_staged": 1}, (17, 15, 5)), ({"persist_staged": 1}, (19, 9, 3)), ({"persist_staged": 1}, (11, 20, 4)),
+    ({"persist_staged": 1}, (14, 13, 1)), ({"persist_staged": 1, "force_ksplit_log2": 1}, (18, 17, 6)),
+    # deep split-K on few tiles (the mid-size class of the rank sweep)
+    ({"force_ksplit_log2": 5}, (20, 20, 12)), ({"force_ksplit_log2": 7}, (22, 22, 16)), ({"force_ksplit_log2": 8, "gemm_feed": 1}, (23, 22, 16)),
+]
+
+
+@pytest.mark.parametrize("knobs,shape", VARIANT_CASES)
+@pytest.mark.parametrize("ready", [True, False])
+def test_kernel_variants_match_numpy(knobs, shape, ready, tuning):
+    ra, rb, k = shape
+    for key, value in knobs.items():
+        tuning(key, value)
+    rng = np.random.default_rng(77 * ra + 5 * rb + k)
+    a = rng.integers(0, 3, size=(2,) * ra).astype(np.float64)
+    b = rng.integers(0, 3, size=(2,) * rb).astype(np.float64)
+    if ready:
+        axes_a, axes_b = list(range(ra - k, ra)), list(range(rb - k, rb))
+    else:  # random axis order: after the operand permutation the OUTPUT interleave (mask_m) is still the plain one,
+        axes_a = [int(x) for x in rng.permutation(ra)[:k]]  # interleaved outputs are covered by the whole-plan tests below
+        axes_b = [int(x) for x in rng.permutation(rb)[:k]]
+    want = np.tensordot(a, b, (axes_a, axes_b))
+    got, ms = _tensordot_device(a, b, axes_a, axes_b)
+    assert ms[2] == 1.0  # DMMA GEMM path
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("knobs", [{"gemm_feed": 1}, {"persist_staged": 1}, {"gemm_feed": 1, "persist_staged": 1, "gemm_min_total": 16}])
+@pytest.mark.parametrize("name", ["vc150_lineflow", "vc170_lineflow", "vc150_mcc_factorflow", "vc200_lineflow"])
+def test_kernel_variants_on_whole_plans(knobs, name, tuning):
+    """Whole contraction trees under the variant kernels: the joins' outputs use arbitrary interleaves of the two
+    operands' free indices (mask_m), which single tensordot calls do not produce.  Bit-identical to the default
+    kernels is not required (the TMA feed permutes the K order inside a 16-wide step); the reference count is."""
+    from conftest import load_golden
+    from tensororder_b200.api import CompiledPlan
+    from tensororder_b200.flatten import flatten_plan
+
+    pp = load_golden(name)
+    for key, value in knobs.items():
+        tuning(key, value)
+    for plan in [pp] + ([pp.variant(0)] if pp.variants else []):
+        cp = CompiledPlan(flatten_plan(plan.as_execution_plan()))
+        cp.upload()
+        got = cp.run()
+        cp.close()
+        want = plan.expected.get("count", pp.expected.get("count"))
+        assert abs(got - want) <= 1e-9 * abs(want), (plan.name, got, want)

@@ -254,7 +254,8 @@ def test_gpu_cli_execution_py_count_and_contraction_time(ref, tmp_path):
     # rank / memory limits and the slicers go through the reference's own option handling
     con = _con_bytes(ref, "vc100_lineflow", tmp_path)
     want = float(_field(_cli("execution.py", [], con, library="numpy")[0], "Count"))
-    for args in (["--rank_limit=10"], ["--mem_limit=100000", "--slicer=b200_mem"], ["--rank_limit=12", "--slice_cutoff=2"]):
+    # (vc100 has max-rank 15: rank 13 = 4 groups / 16 slices, rank 12 = 9 groups / 512 slices; 1.9 MB = 3 groups for b200_mem)
+    for args in (["--rank_limit=13"], ["--mem_limit=1900000", "--slicer=b200_mem"], ["--rank_limit=12", "--slice_cutoff=2"]):
         out_b, err_b, rc = _cli("execution.py", args, con, library="b200")
         assert rc == 0, err_b[-1500:]
         out_n, _, _ = _cli("execution.py", [a for a in args if "b200_mem" not in a], con, library="numpy")
