@@ -42,7 +42,7 @@ Tuning& tuning() {
     static Tuning t = {
         TOB_TUNE_GEMM_MIN_FREE, TOB_TUNE_GEMM_MIN_K, TOB_TUNE_GEMM_MIN_TOTAL, TOB_TUNE_GEMM_SMALLK_MIN_FREE,
         TOB_TUNE_GEMM_SMALLK_MIN_OUT, TOB_TUNE_T1_MAX_K, TOB_TUNE_T32_MAX_K, TOB_TUNE_T32_MIN_OUT,
-        TOB_TUNE_PERSIST_MAX_K, TOB_TUNE_PERSIST_STAGED, TOB_TUNE_GEMM_FEED, TOB_TUNE_SM_GFLOPS, TOB_TUNE_ALONE_FRAC, TOB_TUNE_GEMM_FIX_US, TOB_TUNE_REDUCE_GBS,
+        TOB_TUNE_PERSIST_MAX_K, TOB_TUNE_GEMM_FEED, TOB_TUNE_SM_GFLOPS, TOB_TUNE_ALONE_FRAC, TOB_TUNE_GEMM_FIX_US, TOB_TUNE_REDUCE_GBS,
         TOB_TUNE_REDUCE_FIX_US, TOB_TUNE_MAX_KSPLIT_LOG2, TOB_TUNE_MIN_K_PER_SPLIT_LOG2, -1};
     return t;
 }
@@ -55,7 +55,6 @@ const TuneField kTuneFields[] = {
     {"gemm_smallk_min_out", &Tuning::gemm_smallk_min_out, nullptr}, {"t1_max_k", &Tuning::t1_max_k, nullptr},
     {"t32_max_k", &Tuning::t32_max_k, nullptr}, {"t32_min_out", &Tuning::t32_min_out, nullptr},
     {"persist_max_k", &Tuning::persist_max_k, nullptr}, {"gemm_feed", &Tuning::gemm_feed, nullptr},
-    {"persist_staged", &Tuning::persist_staged, nullptr},
     {"sm_gflops", nullptr, &Tuning::sm_gflops},
     {"alone_frac", nullptr, &Tuning::alone_frac}, {"gemm_fix_us", nullptr, &Tuning::gemm_fix_us},
     {"reduce_gbs", nullptr, &Tuning::reduce_gbs}, {"reduce_fix_us", nullptr, &Tuning::reduce_fix_us},

@@ -121,7 +121,6 @@ struct Tuning {
     int gemm_min_free, gemm_min_k, gemm_min_total, gemm_smallk_min_free, gemm_smallk_min_out;
     int t1_max_k, t32_max_k, t32_min_out;
     int persist_max_k;
-    int persist_staged;     // persistent short-K kernel: 1 = shared-memory-staged epilogue (full-line stores), 0 = direct scatter
     int gemm_feed;          // operand feed of the long-K DMMA GEMM: 1 = 2-D tensor-map copies (TMA), 0 = LDGSTS producer warps
     double sm_gflops, alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us;
     int max_ksplit_log2, min_k_per_split_log2;

@@ -460,11 +460,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
 // (k <= 5) reach 0.65 of HBM there.  256 threads at two CTAs per SM leave 128 registers, so the extra tile
 // state costs no spills (the warp-specialised kernel at 320 threads has no such room: DESIGN.md §4).
 // ------------------------------------------------------------------------------------------------
-// STAGED: the epilogue hands each quarter of the 128x64 tile (one row of warps: 32 rows x 64 columns, 16 KB) through
-// shared memory in C-ADDRESS order, and all 256 threads write it out with 16-byte stores whose 32 lanes cover 512
-// contiguous bytes: the tile's lowest m- and n-bits are the lowest address bits of C, so runs of at
-// least 64 doubles are contiguous.  The direct epilogue scatters 16-byte pieces of eight rows per store instruction.
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB, bool STAGED = false>
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int TK, int STAGES, int MINB>
 __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NT = WM * WN * 32;
@@ -480,16 +476,6 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
     double* Bs = As + STAGES * TM * LDS;
     unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
     unsigned long long* cN = cM + TM;
-    // STAGED: [aLo[64] | aHi[32]] address offsets of a quarter-local index, [lM[32] | lN[64]] local index of (row, col),
-    // then the 2048-double staging buffer
-    constexpr int QROWS = TM / WM;                      // rows of one quarter (32)
-    constexpr int QBITS = (TM_LOG2 - 2) + TN_LOG2;      // 11: quarter-local index bits
-    unsigned long long* aLo = cN + TN;
-    unsigned long long* aHi = aLo + 64;
-    unsigned short* lM = reinterpret_cast<unsigned short*>(aHi + 32);
-    unsigned short* lN = lM + QROWS;
-    double* Cs = reinterpret_cast<double*>(lN + TN);
-    static_assert(!STAGED || (WM == 4 && QBITS == 11), "staged epilogue is written for 128x64 tiles, 4x2 warps");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -498,41 +484,6 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
 
     for (int i = tid; i < TM; i += NT) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
     for (int i = tid; i < TN; i += NT) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
-    if (STAGED) {
-        __syncthreads();
-        // the quarter's 11 address bits (5 row bits, 6 column bits) in ascending C-address order: local index bit b
-        // stands for address bit pos[b]
-        if (tid < 64 + 32 + QROWS + TN) {
-            int pos[QBITS];
-            bool is_m[QBITS];
-            int src[QBITS];
-            int im = 0, in = 0;
-            for (int b = 0; b < QBITS; b++) {
-                const unsigned long long am = im < TM_LOG2 - 2 ? cM[1 << im] : ~0ull, an = in < TN_LOG2 ? cN[1 << in] : ~0ull;
-                if (am < an) { pos[b] = 63 - __clzll(am); is_m[b] = true; src[b] = im++; }
-                else { pos[b] = 63 - __clzll(an); is_m[b] = false; src[b] = in++; }
-            }
-            if (tid < 64) {  // low six local bits -> address offset
-                unsigned long long a = 0;
-                for (int b = 0; b < 6; b++) a |= (unsigned long long)((tid >> b) & 1) << pos[b];
-                aLo[tid] = a;
-            } else if (tid < 96) {
-                unsigned long long a = 0;
-                for (int b = 6; b < QBITS; b++) a |= (unsigned long long)(((tid - 64) >> (b - 6)) & 1) << pos[b];
-                aHi[tid - 64] = a;
-            } else if (tid < 96 + QROWS) {
-                unsigned l = 0;
-                for (int b = 0; b < QBITS; b++)
-                    if (is_m[b]) l |= (((tid - 96) >> src[b]) & 1u) << b;
-                lM[tid - 96] = (unsigned short)l;
-            } else {
-                unsigned l = 0;
-                for (int b = 0; b < QBITS; b++)
-                    if (!is_m[b]) l |= (((tid - 96 - QROWS) >> src[b]) & 1u) << b;
-                lN[tid - 96 - QROWS] = (unsigned short)l;
-            }
-        }
-    }
 
     const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
     const unsigned long long tiles = tilesM * tilesN;
@@ -649,37 +600,6 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
             decode(c_id, split, tile_m, tile_n);
             double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
             const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
-            if (STAGED) {
-#pragma unroll 1
-                for (int q = 0; q < WM; q++) {
-                    if (wm == q) {  // this row of warps owns rows q*32 .. q*32+31 of the tile
-#pragma unroll
-                        for (int i = 0; i < MB; i++) {
-                            const unsigned lr = lM[i * 8 + g];
-#pragma unroll
-                            for (int j = 0; j < NB; j++) {
-                                const int col = wn * WTN + j * 8 + 2 * t;
-                                if (vec) {
-                                    *reinterpret_cast<double2*>(Cs + (lr | lN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
-                                } else {
-                                    Cs[lr | lN[col]] = acc[i][j][0];
-                                    Cs[lr | lN[col + 1]] = acc[i][j][1];
-                                }
-                                acc[i][j][0] = acc[i][j][1] = 0.0;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    double* dst = Cout + (cbase | cM[q * QROWS]);
-#pragma unroll
-                    for (int e = 0; e < (1 << QBITS) / (2 * NT); e++) {
-                        const int idx = e * 2 * NT + tid * 2;
-                        const double2 v = *reinterpret_cast<const double2*>(Cs + idx);
-                        *reinterpret_cast<double2*>(dst + (aLo[idx & 63] | aHi[idx >> 6])) = v;
-                    }
-                    __syncthreads();
-                }
-            } else {
 #pragma unroll
             for (int i = 0; i < MB; i++) {
                 const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
@@ -694,7 +614,6 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
                     }
                     acc[i][j][0] = acc[i][j][1] = 0.0;
                 }
-            }
             }
             c_kt = 0;
             c_id += gridDim.x;
@@ -1106,8 +1025,6 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
 #define GEMM_76_P k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2>
-#define GEMM_76_PS k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2, true>
-constexpr size_t kStagedEpilogueBytes = (64 + 32) * 8 + (32 + 64) * 2 + 2048 * 8 + 64;
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 // residue-arithmetic instantiations (entry type bigint)
@@ -1128,8 +1045,6 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_PS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(gemm_smem_bytes<7, 6, 16, 3>() + kStagedEpilogueBytes));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
@@ -1427,10 +1342,9 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             const int kk = op.k - op.ksplit_log2;  // log2 of the K range one CTA walks
             if (kk <= T.persist_max_k && blocks > 2ull * (unsigned long long)num_sms())
                 // short K, more tiles than CTA slots (the store-bound joins): persistent CTAs prefetch the next tiles
-                if (T.persist_staged)
-                    GEMM_76_PS<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>() + kStagedEpilogueBytes, stream>>>(p);
-                else
-                    GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
+                // (a shared-memory-staged epilogue writing 512-byte runs was measured in round 2 and is 25-30 % SLOWER than
+                // the direct 16-byte scatter: profiles/r02b_kernel_lab_tma_staged.md — its barriers serialise the tile)
+                GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
             else if (kk >= 8) {
                 // warp-specialised pipeline, 4-stage ring, mbarrier full/empty stages.  Feed: tensor-map copies from one
                 // elected thread (gemm_feed = 1) or LDGSTS from two producer warps (0); operands that carry a per-slice

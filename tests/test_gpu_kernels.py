@@ -138,10 +138,8 @@ VARIANT_CASES = [
     ({"gemm_feed": 0}, (18, 16, 9)), ({"gemm_feed": 1}, (18, 16, 9)), ({"gemm_feed": 1}, (21, 18, 9)),
     ({"gemm_feed": 1}, (22, 22, 16)), ({"gemm_feed": 1}, (17, 17, 10)), ({"gemm_feed": 1, "force_ksplit_log2": 2}, (19, 18, 11)),
     ({"gemm_feed": 1}, (16, 21, 10)),  # swapped operands (n > m)
-    # short-K persistent kernel: direct vs shared-memory-staged epilogue, every LOW-bit pattern of the output interleave
-    ({"persist_staged": 0}, (16, 14, 4)), ({"persist_staged": 1}, (16, 14, 4)), ({"persist_staged": 1}, (15, 13, 2)),
-    ({"persist_staged": 1}, (17, 15, 5)), ({"persist_staged": 1}, (19, 9, 3)), ({"persist_staged": 1}, (11, 20, 4)),
-    ({"persist_staged": 1}, (14, 13, 1)), ({"persist_staged": 1, "force_ksplit_log2": 1}, (18, 17, 6)),
+    # short-K persistent kernel under a forced split
+    ({"force_ksplit_log2": 1}, (18, 17, 6)), ({"persist_max_k": -1}, (16, 14, 4)),
     # deep split-K on few tiles (the mid-size class of the rank sweep)
     ({"force_ksplit_log2": 5}, (20, 20, 12)), ({"force_ksplit_log2": 7}, (22, 22, 16)), ({"force_ksplit_log2": 8, "gemm_feed": 1}, (23, 22, 16)),
 ]
@@ -167,7 +165,7 @@ def test_kernel_variants_match_numpy(knobs, shape, ready, tuning):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("knobs", [{"gemm_feed": 1}, {"persist_staged": 1}, {"gemm_feed": 1, "persist_staged": 1, "gemm_min_total": 16}])
+@pytest.mark.parametrize("knobs", [{"gemm_feed": 1}, {"gemm_feed": 1, "gemm_min_total": 16}, {"max_ksplit_log2": 0}])
 @pytest.mark.parametrize("name", ["vc150_lineflow", "vc170_lineflow", "vc150_mcc_factorflow", "vc200_lineflow"])
 def test_kernel_variants_on_whole_plans(knobs, name, tuning):
     """Whole contraction trees under the variant kernels: the joins' outputs use arbitrary interleaves of the two
