@@ -275,11 +275,11 @@ def measure_fp64_peak(torch, dev, n=8192, reps=6):
 
 
 def lib_build_id():
-    from tensororder_b200 import cabi
-
+    """Identity of the kernel sources the library was built from (tools/ncu_summary.py stamps its captures with it)."""
     h = hashlib.sha256()
-    with open(cabi.LIB_PATH, "rb") as f:
-        h.update(f.read())
+    for name in ("tob_kernels.cu", "tob_kernels.cuh", "tob_dispatch_table.h"):
+        with open(os.path.join(REPO, "tensororder_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
     return h.hexdigest()[:16]
 
 
@@ -665,7 +665,10 @@ def b200_arm(args, rank, world, local_rank):
                 "peak_round1_calibration": FP64_CUBLAS_CALIBRATION, "frac_of_round1_calibration": achieved / FP64_CUBLAS_CALIBRATION,
                 "dmma_pipe_peak": FP64_DMMA_PIPE, "frac_of_dmma_pipe": achieved / FP64_DMMA_PIPE,
                 "measured": "separate sequential pass over rank 0's instances after the timed steps, one CUDA-event pair per GEMM launch",
-                "gemm_ms_rank0": gemm_ms, "share_of_step": gemm_ms / ms_per_step, "traffic_note": traffic_note,
+                "gemm_ms_rank0": gemm_ms, "share_of_step": gemm_ms / seq_ms if seq_ms > 0 else None,
+                "share_note": "GEMM event time / device time of the same sequential pass on rank 0 (comparable with the "
+                              "serialised ncu launch list); in the timed (asynchronous) steps everything else overlaps the GEMMs",
+                "traffic_note": traffic_note,
             }
         if world == 1 and not args.no_large:
             # beyond what the CPU arm can time: the largest family members, one pass each (device time)

@@ -171,6 +171,12 @@ int tob_plan_set_stream(tob_plan* plan, void* stream);
 int64_t tob_plan_num_ops(const tob_plan* plan);
 int tob_plan_profile(tob_plan* plan, uint64_t slice, float* ms_per_op, int64_t n_ops, double* result);
 
+/* Verification aids: run the first n_ops ops (slice-invariant list, then the per-slice list) of one slice
+ * sequentially on one stream and wait; read doubles back from the leaf region (space 0) or the arena (1).  With
+ * them every join's output is compared with the numpy interpreter of the same program (tools/verify_ops.py). */
+int tob_plan_debug_run(tob_plan* plan, uint64_t slice, int64_t n_ops);
+int tob_plan_debug_read(tob_plan* plan, int32_t space, int64_t offset, int64_t n, double* out);
+
 void tob_plan_destroy(tob_plan* plan);
 
 /*

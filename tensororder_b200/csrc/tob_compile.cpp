@@ -39,11 +39,30 @@ static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // Kernel choice for a canonical join  C[2^(m+n)] = A[2^m x 2^k] . B[2^n x 2^k]^T
 // ------------------------------------------------------------------------------------------------
 Tuning& tuning() {
-    static Tuning t = {
-        TOB_TUNE_GEMM_MIN_FREE, TOB_TUNE_GEMM_MIN_K, TOB_TUNE_GEMM_MIN_TOTAL, TOB_TUNE_GEMM_SMALLK_MIN_FREE,
-        TOB_TUNE_GEMM_SMALLK_MIN_OUT, TOB_TUNE_T1_MAX_K, TOB_TUNE_T32_MAX_K, TOB_TUNE_T32_MIN_OUT,
-        TOB_TUNE_PERSIST_MAX_K, TOB_TUNE_GEMM_FEED, TOB_TUNE_SM_GFLOPS, TOB_TUNE_ALONE_FRAC, TOB_TUNE_GEMM_FIX_US, TOB_TUNE_REDUCE_GBS,
-        TOB_TUNE_REDUCE_FIX_US, TOB_TUNE_MAX_KSPLIT_LOG2, TOB_TUNE_MIN_K_PER_SPLIT_LOG2, -1};
+    static Tuning t = [] {
+        Tuning x;
+        x.gemm_min_free = TOB_TUNE_GEMM_MIN_FREE;
+        x.gemm_min_k = TOB_TUNE_GEMM_MIN_K;
+        x.gemm_smallk_min_free = TOB_TUNE_GEMM_SMALLK_MIN_FREE;
+        const int by_k[17] = TOB_TUNE_GEMM_MIN_OUT_BY_K;
+        for (int i = 0; i < 17; i++) x.gemm_min_out[i] = by_k[i];
+        x.t1_max_k = TOB_TUNE_T1_MAX_K;
+        x.t1_small_out = TOB_TUNE_T1_SMALL_OUT;
+        x.t1_small_max_k = TOB_TUNE_T1_SMALL_MAX_K;
+        x.t32_max_k = TOB_TUNE_T32_MAX_K;
+        x.t32_min_out = TOB_TUNE_T32_MIN_OUT;
+        x.persist_max_k = TOB_TUNE_PERSIST_MAX_K;
+        x.gemm_feed = TOB_TUNE_GEMM_FEED;
+        x.sm_gflops = TOB_TUNE_SM_GFLOPS;
+        x.alone_frac = TOB_TUNE_ALONE_FRAC;
+        x.gemm_fix_us = TOB_TUNE_GEMM_FIX_US;
+        x.reduce_gbs = TOB_TUNE_REDUCE_GBS;
+        x.reduce_fix_us = TOB_TUNE_REDUCE_FIX_US;
+        x.max_ksplit_log2 = TOB_TUNE_MAX_KSPLIT_LOG2;
+        x.min_k_per_split_log2 = TOB_TUNE_MIN_K_PER_SPLIT_LOG2;
+        x.force_ksplit_log2 = -1;
+        return x;
+    }();
     return t;
 }
 
@@ -51,8 +70,9 @@ namespace {
 struct TuneField { const char* key; int Tuning::*i; double Tuning::*d; };
 const TuneField kTuneFields[] = {
     {"gemm_min_free", &Tuning::gemm_min_free, nullptr}, {"gemm_min_k", &Tuning::gemm_min_k, nullptr},
-    {"gemm_min_total", &Tuning::gemm_min_total, nullptr}, {"gemm_smallk_min_free", &Tuning::gemm_smallk_min_free, nullptr},
-    {"gemm_smallk_min_out", &Tuning::gemm_smallk_min_out, nullptr}, {"t1_max_k", &Tuning::t1_max_k, nullptr},
+    {"gemm_smallk_min_free", &Tuning::gemm_smallk_min_free, nullptr},
+    {"t1_max_k", &Tuning::t1_max_k, nullptr}, {"t1_small_out", &Tuning::t1_small_out, nullptr},
+    {"t1_small_max_k", &Tuning::t1_small_max_k, nullptr},
     {"t32_max_k", &Tuning::t32_max_k, nullptr}, {"t32_min_out", &Tuning::t32_min_out, nullptr},
     {"persist_max_k", &Tuning::persist_max_k, nullptr}, {"gemm_feed", &Tuning::gemm_feed, nullptr},
     {"sm_gflops", nullptr, &Tuning::sm_gflops},
@@ -61,9 +81,20 @@ const TuneField kTuneFields[] = {
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
 };
+// "gemm_min_out" sets every k at once, "gemm_min_out.<k>" one entry
+int min_out_index(const char* key) {
+    const std::string s = key ? key : "";
+    if (s == "gemm_min_out") return 17;
+    if (s.rfind("gemm_min_out.", 0) != 0) return -1;
+    const int k = atoi(s.c_str() + 13);
+    return (k >= 0 && k <= 16) ? k : -1;
+}
 }  // namespace
 
 bool tuning_set(const char* key, double value) {
+    const int mo = min_out_index(key);
+    if (mo == 17) { for (int i = 1; i < 17; i++) tuning().gemm_min_out[i] = (int)value; return true; }
+    if (mo >= 0) { tuning().gemm_min_out[mo] = (int)value; return true; }
     for (const TuneField& f : kTuneFields)
         if (key && std::string(key) == f.key) {
             if (f.i) tuning().*(f.i) = (int)value; else tuning().*(f.d) = value;
@@ -72,6 +103,8 @@ bool tuning_set(const char* key, double value) {
     return false;
 }
 bool tuning_get(const char* key, double* value) {
+    const int mo = min_out_index(key);
+    if (mo >= 0 && mo <= 16) { *value = tuning().gemm_min_out[mo]; return true; }
     for (const TuneField& f : kTuneFields)
         if (key && std::string(key) == f.key) {
             *value = f.i ? (double)(tuning().*(f.i)) : tuning().*(f.d);
@@ -110,10 +143,11 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     op->ksplit_log2 = 0;
     // k >= gemm_min_k: the DMMA pipeline proper.  1 <= k < gemm_min_k with a large two-sided output (outer-product-
     // like joins): the same kernel with a zero-filled K step, i.e. a tiled store kernel with full operand reuse,
-    // instead of one thread per output re-reading both rows from L2.  Thresholds: tob_dispatch_table.h (measured).
-    const bool gemm_ok = (k >= T.gemm_min_k && m >= T.gemm_min_free && n >= T.gemm_min_free && (m + n + k) >= T.gemm_min_total) ||
-                         (k >= 1 && k < T.gemm_min_k && m >= T.gemm_smallk_min_free && n >= T.gemm_smallk_min_free &&
-                          (m + n) >= T.gemm_smallk_min_out);
+    // instead of one thread per output re-reading both rows from L2.  The crossover against the generic kernels is
+    // a measured table by k (tob_dispatch_table.h): few outputs with a long K belong to the warp / CTA-per-output
+    // kernels, whose K split fills the machine where one or two GEMM tiles cannot.
+    const int min_free = k >= T.gemm_min_k ? T.gemm_min_free : T.gemm_smallk_min_free;
+    const bool gemm_ok = k >= 1 && m >= min_free && n >= min_free && (m + n) >= T.gemm_min_out[std::min(k, 16)];
     if (kernel_policy != 1 && gemm_ok) {
         op->kind = OP_GEMM;
         op->tm_log2 = std::min(m, 7);
@@ -133,7 +167,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     }
     op->kind = OP_GENERIC;
     const int outs = m + n;
-    if (k <= T.t1_max_k) {
+    if (k <= ((outs <= T.t1_small_out) ? T.t1_small_max_k : T.t1_max_k)) {
         op->threads_per_out = 1;
     } else if (outs >= T.t32_min_out && k <= T.t32_max_k) {
         op->threads_per_out = 32;

@@ -1079,6 +1079,49 @@ int tob_plan_profile(tob_plan* p, uint64_t slice, float* ms_per_op, int64_t n_op
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-op verification (tools/verify_ops.py, tests): run a prefix of one slice's program sequentially on lane 0,
+// then read tensors back, so every join's output can be held against the numpy interpreter of the same program
+// ------------------------------------------------------------------------------------------------
+int tob_plan_debug_run(tob_plan* p, uint64_t slice, int64_t n_ops) {
+    if (!p || !p->uploaded) { set_error("tob_plan_debug_run: plan is not uploaded"); return TOB_E_INVALID; }
+    if (slice >= tob_plan_num_slices(p) || n_ops < 0 || n_ops > tob_plan_num_ops(p)) { set_error("bad debug arguments"); return TOB_E_INVALID; }
+    int rc = ensure_device(p->device);
+    if (rc != TOB_OK) return rc;
+    int launches = 0;
+    Lane& L0 = p->lane[0];
+    p->in_flight = true;
+    p->h_state[0].next_slice = slice;
+    p->h_state[0].stride = 1;
+    p->h_state[0].slot = 0;
+    p->h_state[0].slot_stride = 1;
+    CUDA_TRY(cudaMemcpyAsync(L0.d_state, p->h_state, sizeof(DevState), cudaMemcpyHostToDevice, L0.stream));
+    int64_t i = 0;
+    for (const Op& op : p->prog.invariant_ops) {
+        if (i++ >= n_ops) break;
+        CUDA_TRY(launch_op(p, L0, op, &launches));
+    }
+    CUDA_TRY(launch_begin(p, L0, &launches));
+    for (const Op& op : p->prog.slice_ops) {
+        if (i++ >= n_ops) break;
+        CUDA_TRY(launch_op(p, L0, op, &launches));
+    }
+    CUDA_TRY(cudaStreamSynchronize(L0.stream));
+    p->in_flight = false;
+    return TOB_OK;
+}
+
+int tob_plan_debug_read(tob_plan* p, int32_t space, int64_t offset, int64_t n, double* out) {
+    if (!p || !p->uploaded || !out || offset < 0 || n < 0) { set_error("bad debug arguments"); return TOB_E_INVALID; }
+    const int64_t limit = space == 0 ? p->prog.leaf_doubles : p->prog.arena_doubles;
+    if (offset + n > limit) { set_error("tob_plan_debug_read: range outside the region"); return TOB_E_INVALID; }
+    int rc = ensure_device(p->device);
+    if (rc != TOB_OK) return rc;
+    const double* base = space == 0 ? p->d_leaves : p->lane[0].d_arena;
+    CUDA_TRY(cudaMemcpy(out, base + offset, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return TOB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone tensordot / permute
 // ------------------------------------------------------------------------------------------------
 int tob_permute_device(const double* in, double* out, int32_t rank, const int32_t* perm, void* stream_v, float* ms) {

@@ -118,8 +118,9 @@ void set_num_sms(int n);
 // Per-join dispatch parameters: defaults come from the measured table tob_dispatch_table.h (generated by
 // tools/fit_dispatch.py); tob_tuning_set overrides single values at run time (experiments, the fit itself).
 struct Tuning {
-    int gemm_min_free, gemm_min_k, gemm_min_total, gemm_smallk_min_free, gemm_smallk_min_out;
-    int t1_max_k, t32_max_k, t32_min_out;
+    int gemm_min_free, gemm_min_k, gemm_smallk_min_free;
+    int gemm_min_out[17];   // by k (k > 16 uses [16]): a join runs on the DMMA GEMM kernel when m + n >= gemm_min_out[k]
+    int t1_max_k, t1_small_out, t1_small_max_k, t32_max_k, t32_min_out;
     int persist_max_k;
     int gemm_feed;          // operand feed of the long-K DMMA GEMM: 1 = 2-D tensor-map copies (TMA), 0 = LDGSTS producer warps
     double sm_gflops, alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us;

@@ -165,7 +165,7 @@ def test_kernel_variants_match_numpy(knobs, shape, ready, tuning):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("knobs", [{"gemm_feed": 1}, {"gemm_feed": 1, "gemm_min_total": 16}, {"max_ksplit_log2": 0}])
+@pytest.mark.parametrize("knobs", [{"gemm_feed": 1}, {"gemm_feed": 1, "gemm_min_out": 12}, {"max_ksplit_log2": 0}])
 @pytest.mark.parametrize("name", ["vc150_lineflow", "vc170_lineflow", "vc150_mcc_factorflow", "vc200_lineflow"])
 def test_kernel_variants_on_whole_plans(knobs, name, tuning):
     """Whole contraction trees under the variant kernels: the joins' outputs use arbitrary interleaves of the two

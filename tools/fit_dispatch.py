@@ -42,9 +42,9 @@ def tget(key):
     return v.value
 
 
-KEYS = ["gemm_min_free", "gemm_min_k", "gemm_min_total", "gemm_smallk_min_free", "gemm_smallk_min_out", "t1_max_k",
+KEYS = ["gemm_min_free", "gemm_min_k", "gemm_smallk_min_free", "t1_max_k", "t1_small_out", "t1_small_max_k",
         "t32_max_k", "t32_min_out", "persist_max_k", "sm_gflops", "alone_frac", "gemm_fix_us", "reduce_gbs",
-        "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2"]
+        "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2"] + ["gemm_min_out.%d" % i for i in range(17)]
 for k_ in KEYS:
     DEFAULTS[k_] = tget(k_)
 
@@ -94,7 +94,7 @@ def model_us(m, n, k, c):
     return lib.tob_gemm_time_model_us(m, n, k, min(m, 7), min(n, 6), c)
 
 
-out = {"when": datetime.datetime.utcnow().isoformat() + "Z", "gpu": torch.cuda.get_device_name(0)}
+out = {"when": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ"), "gpu": torch.cuda.get_device_name(0)}
 
 # ---------------------------------------------------------------------------------------------------
 # A. split-K
@@ -158,51 +158,42 @@ for (m, n, k) in shapes:
 out["splitk_picks"] = picks
 
 # ---------------------------------------------------------------------------------------------------
-# B. generic <-> GEMM crossover
+# B. generic <-> GEMM crossover, by k: the smallest m + n from which the GEMM kernel is at least as fast as the best
+#    generic kernel for that and every larger measured output
 # ---------------------------------------------------------------------------------------------------
 cross = []
-tset("gemm_min_total", 0)
-tset("gemm_smallk_min_out", 0)
-tset("gemm_smallk_min_free", 7)
-for k in ([4, 6, 8] if quick else [4, 5, 6, 7, 8, 10]):
-    for tot in range(16, 25):
-        m = (tot - k + 1) // 2
-        n = tot - k - m
-        if n < 6:
+tset("gemm_min_out", 0)  # every k: GEMM whenever the free sides allow a tile
+for k in ([2, 4, 8] if quick else [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16]):
+    lo = 14 if k < 4 else 12
+    for outs in range(lo, 23 if k <= 8 else 21):
+        m = (outs + 1) // 2
+        n = outs - m
+        if n < (7 if k < 4 else 6):
             continue
         g, kind_g = time_join(m, n, k, policy=0)
-        s, _ = time_join(m, n, k, policy=1)
-        cross.append({"m": m, "n": n, "k": k, "total": tot, "gemm_us": g, "generic_us": s, "gemm_kind": kind_g})
-for k in (1, 2, 3):
-    for outs in range(14, 23, 2):
-        m = n = outs // 2
-        g, kind_g = time_join(m, n, k, policy=0)
-        s, _ = time_join(m, n, k, policy=1)
-        cross.append({"m": m, "n": n, "k": k, "outs": outs, "gemm_us": g, "generic_us": s, "gemm_kind": kind_g})
+        s_, _ = time_join(m, n, k, policy=1)
+        cross.append({"m": m, "n": n, "k": k, "outs": outs, "gemm_us": g, "generic_us": s_, "gemm_kind": kind_g})
 restore()
 out["crossover"] = cross
-# smallest total from which the GEMM kernel wins for every k >= 4 row measured at that total and above
-tot_wins = {}
-for r in cross:
-    if "total" in r and r["gemm_kind"] == 1:
-        tot_wins.setdefault(r["total"], []).append(r["gemm_us"] <= r["generic_us"] * 1.02)
-gemm_min_total = int(DEFAULTS["gemm_min_total"])
-for tot in sorted(tot_wins, reverse=True):
-    if all(tot_wins[tot]):
-        gemm_min_total = tot
-    else:
-        break
-outs_wins = {}
-for r in cross:
-    if "outs" in r and r["gemm_kind"] == 1:
-        outs_wins.setdefault(r["outs"], []).append(r["gemm_us"] <= r["generic_us"] * 1.02)
-smallk_min_out = int(DEFAULTS["gemm_smallk_min_out"])
-for o in sorted(outs_wins, reverse=True):
-    if all(outs_wins[o]):
-        smallk_min_out = o
-    else:
-        break
-print("crossover: gemm_min_total ->", gemm_min_total, " gemm_smallk_min_out ->", smallk_min_out)
+min_out = [99] + [int(DEFAULTS["gemm_min_out.%d" % i]) for i in range(1, 17)]
+for k in sorted(set(r["k"] for r in cross)):
+    rs = sorted([r for r in cross if r["k"] == k and r["gemm_kind"] == 1], key=lambda r: -r["outs"])
+    best = None
+    for r in rs:
+        if r["gemm_us"] <= r["generic_us"] * 1.03:
+            best = r["outs"]
+        else:
+            break
+    if best is not None:
+        min_out[k] = best
+    elif rs:
+        min_out[k] = rs[0]["outs"] + 1
+for k in range(1, 17):  # unmeasured k: the nearest measured neighbour below
+    if k not in set(r["k"] for r in cross):
+        below = [q for q in set(r["k"] for r in cross) if q < k]
+        if below:
+            min_out[k] = min_out[max(below)]
+print("crossover: gemm_min_out by k ->", min_out)
 for r in cross:
     print("  m=%d n=%d k=%d  gemm %.1f us  generic %.1f us  (%s)" % (r["m"], r["n"], r["k"], r["gemm_us"], r["generic_us"],
                                                                   "gemm kernel" if r["gemm_kind"] == 1 else "generic both"))
@@ -227,7 +218,9 @@ for outs in (12, 16, 20):
         classes.append({"outs": outs, "k": k, **res})
         print("  generic classes outs=2^%d k=%d: %s" % (outs, k, {a: round(b, 1) for a, b in res.items()}))
 out["generic_classes"] = classes
-t1_max_k = max([r["k"] for r in classes if "t1" in r and r["t1"] <= min(r["t32"], r["t256"]) * 1.02] or [int(DEFAULTS["t1_max_k"])])
+t1_max_k = max([r["k"] for r in classes if r["outs"] >= 16 and "t1" in r and r["t1"] <= min(r["t32"], r["t256"]) * 1.02] or [int(DEFAULTS["t1_max_k"])])
+small = [r for r in classes if r["outs"] == 12 and "t1" in r]
+t1_small_max_k = max([r["k"] for r in small if r["t1"] <= min(r["t32"], r["t256"]) * 1.02] or [3])
 t32_max_k = max([r["k"] for r in classes if r["outs"] >= 12 and r["t32"] <= r["t256"] * 1.02] or [int(DEFAULTS["t32_max_k"])])
 persist = []
 for k in range(1, 8):
@@ -244,9 +237,11 @@ persist_max_k = max([r["k"] for r in persist if r["persistent_us"] <= r["one_til
 
 # ---------------------------------------------------------------------------------------------------
 table = {
-    "GEMM_MIN_FREE": int(DEFAULTS["gemm_min_free"]), "GEMM_MIN_K": int(DEFAULTS["gemm_min_k"]), "GEMM_MIN_TOTAL": gemm_min_total,
-    "GEMM_SMALLK_MIN_FREE": int(DEFAULTS["gemm_smallk_min_free"]), "GEMM_SMALLK_MIN_OUT": smallk_min_out,
-    "T1_MAX_K": min(t1_max_k, 6), "T32_MAX_K": t32_max_k, "T32_MIN_OUT": int(DEFAULTS["t32_min_out"]),
+    "GEMM_MIN_FREE": int(DEFAULTS["gemm_min_free"]), "GEMM_MIN_K": int(DEFAULTS["gemm_min_k"]),
+    "GEMM_SMALLK_MIN_FREE": int(DEFAULTS["gemm_smallk_min_free"]),
+    "GEMM_MIN_OUT_BY_K": "{" + ", ".join(str(v) for v in min_out) + "}",
+    "T1_MAX_K": min(t1_max_k, 6), "T1_SMALL_OUT": 13, "T1_SMALL_MAX_K": min(t1_small_max_k, 6),
+    "T32_MAX_K": t32_max_k, "T32_MIN_OUT": int(DEFAULTS["t32_min_out"]),
     "PERSIST_MAX_K": persist_max_k, "SM_GFLOPS": DEFAULTS["sm_gflops"], "ALONE_FRAC": fit["alone_frac"],
     "GEMM_FIX_US": float(fit["gemm_fix_us"]), "REDUCE_GBS": float(fit["reduce_gbs"]), "REDUCE_FIX_US": float(fit["reduce_fix_us"]),
     "MAX_KSPLIT_LOG2": int(DEFAULTS["max_ksplit_log2"]), "MIN_K_PER_SPLIT_LOG2": int(DEFAULTS["min_k_per_split_log2"]),
@@ -265,7 +260,8 @@ for ln in src:
         if name in table:
             comment = ln[ln.index("//"):] if "//" in ln else ""
             v = table[name]
-            ln = ("#define TOB_TUNE_%s %s" % (name, ("%d" % v) if isinstance(v, int) else ("%.4g" % v if v < 100 else "%.1f" % v))).ljust(42) + comment
+            txt = v if isinstance(v, str) else (("%d" % v) if isinstance(v, int) else ("%.4g" % v if v < 100 else "%.1f" % v))
+            ln = ("#define TOB_TUNE_%s %s" % (name, txt)).ljust(42) + ("  " + comment if isinstance(v, str) else comment)
     lines.append(ln)
 open(os.path.join(REPO, "gpurun_out", "tob_dispatch_table.h"), "w").write("\n".join(lines))
 print("wrote gpurun_out/dispatch_fit.json and gpurun_out/tob_dispatch_table.h")

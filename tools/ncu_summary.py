@@ -36,8 +36,10 @@ def to_float(x):
 
 def main():
     tag = sys.argv[1]
-    so = os.path.join(REPO, "tensororder_b200", "csrc", "libtob200.so")
-    build = hashlib.sha256(open(so, "rb").read()).hexdigest()[:16]
+    h = hashlib.sha256()  # identity of the kernel sources (same recipe as bench.py lib_build_id)
+    for name in ("tob_kernels.cu", "tob_kernels.cuh", "tob_dispatch_table.h"):
+        h.update(open(os.path.join(REPO, "tensororder_b200", "csrc", name), "rb").read())
+    build = h.hexdigest()[:16]
     for rep in sys.argv[2:]:
         header, rows, units = raw_rows(rep)
         name = os.path.basename(rep)[:-len(".ncu-rep")]
