@@ -52,7 +52,6 @@ Tuning& tuning() {
         x.t32_max_k = TOB_TUNE_T32_MAX_K;
         x.t32_min_out = TOB_TUNE_T32_MIN_OUT;
         x.persist_max_k = TOB_TUNE_PERSIST_MAX_K;
-        x.gemm_feed = TOB_TUNE_GEMM_FEED;
         x.sm_gflops = TOB_TUNE_SM_GFLOPS;
         x.alone_frac = TOB_TUNE_ALONE_FRAC;
         x.gemm_fix_us = TOB_TUNE_GEMM_FIX_US;
@@ -74,7 +73,7 @@ const TuneField kTuneFields[] = {
     {"t1_max_k", &Tuning::t1_max_k, nullptr}, {"t1_small_out", &Tuning::t1_small_out, nullptr},
     {"t1_small_max_k", &Tuning::t1_small_max_k, nullptr},
     {"t32_max_k", &Tuning::t32_max_k, nullptr}, {"t32_min_out", &Tuning::t32_min_out, nullptr},
-    {"persist_max_k", &Tuning::persist_max_k, nullptr}, {"gemm_feed", &Tuning::gemm_feed, nullptr},
+    {"persist_max_k", &Tuning::persist_max_k, nullptr},
     {"sm_gflops", nullptr, &Tuning::sm_gflops},
     {"alone_frac", nullptr, &Tuning::alone_frac}, {"gemm_fix_us", nullptr, &Tuning::gemm_fix_us},
     {"reduce_gbs", nullptr, &Tuning::reduce_gbs}, {"reduce_fix_us", nullptr, &Tuning::reduce_fix_us},

@@ -122,7 +122,6 @@ struct Tuning {
     int gemm_min_out[17];   // by k (k > 16 uses [16]): a join runs on the DMMA GEMM kernel when m + n >= gemm_min_out[k]
     int t1_max_k, t1_small_out, t1_small_max_k, t32_max_k, t32_min_out;
     int persist_max_k;
-    int gemm_feed;          // operand feed of the long-K DMMA GEMM: 1 = 2-D tensor-map copies (TMA), 0 = LDGSTS producer warps
     double sm_gflops, alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us;
     int max_ksplit_log2, min_k_per_split_log2;
     int force_ksplit_log2;  // >= 0: experiments only — every split-capable GEMM uses this split

@@ -15,8 +15,6 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
-
 #include "tob_kernels.cuh"
 
 namespace tob {
@@ -827,189 +825,13 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
 
 
 // ------------------------------------------------------------------------------------------------
-// TMA-fed variant of the warp-specialised GEMM.  Both operands are dense 2-D boxes (rows x K, K contiguous), so
-// ONE elected thread feeds a stage with two tensor-map copies (cp.async.bulk.tensor.2d, SASS UTMALDG) that land
-// a 128 x 16 box of A and a 64 x 16 box of B in 128-byte-swizzled shared memory and complete the stage's `full`
-// mbarrier by transaction bytes: no per-thread address arithmetic, no LDGSTS issue slots, one producer warp
-// instead of two (288 threads: 112 registers per thread instead of 96 at two CTAs per SM).
-//
-// Fragment addressing under CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk index XOR (row & 7)): the 8x4 DMMA
-// fragment of k4-step j reads, for lane (g = row & 7, t), chunk (j + 4 * (t >> 1)) ^ g, element t & 1.  The two
-// chunks of a step are FOUR apart, so the sixteen lanes of a half warp (g = 0..3 or 4..7, t = 0..3) hit sixteen
-// distinct 8-byte slots of the 128-byte bank row: conflict-free LDS.64.  This is a permutation of the K order
-// inside one 16-wide K step, applied identically to A and B, so the products that meet are the right ones.
+// A TMA-fed variant of this kernel (2-D tensor maps, cp.async.bulk.tensor.2d / UTMALDG.2D from one elected thread, 128-byte
+// swizzle, one producer warp) was built and measured in round 2 and is NOT part of the build: it ran 0.4-2.3 % slower than
+// the two-producer LDGSTS feed on every join measured (profiles/r02b_kernel_lab_tma_staged.md; ncu side by side:
+// profiles/r02c_gemm_11_11_12{,_tma}_ncu_summary.json — same DRAM traffic, 2.5x the shared-memory bank conflicts), and it
+// returned slightly wrong counts when two slice lanes ran it concurrently (profiles/r02d_tma_race_*.log; never with the
+// LDGSTS feed).  The code is in the history: commit "TMA-fed DMMA GEMM variant" (k_gemm_dmma_tma).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, bool EXACT = false>
-__global__ void __launch_bounds__(WM * WN * 32 + 32, MINB)
-k_gemm_dmma_tma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, KParams p) {
-    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
-    constexpr int NC = WM * WN * 32;  // consumer threads
-    constexpr int TK = 16, K4 = TK / 4;
-    constexpr int WTM = TM / WM, WTN = TN / WN;
-    constexpr int MB = WTM / 8, NB = WTN / 8;
-    constexpr unsigned STAGE_BYTES = (TM + TN) * TK * 8;
-    extern __shared__ unsigned char smem_raw[];
-    // swizzled TMA destinations need 1024-byte alignment
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    double* As = reinterpret_cast<double*>(base);
-    double* Bs = As + STAGES * TM * TK;
-    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * TK);
-    unsigned long long* cN = cM + TM;
-    unsigned long long* full = cN + TN;
-    unsigned long long* empty = full + STAGES;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = p.k, ks = p.ksplit_log2;
-
-    const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
-    const unsigned long long tiles = tilesM * tilesN;
-    const unsigned long long id = blockIdx.x;
-    const unsigned long long split = id / tiles, tid_in = id % tiles;
-    const unsigned long long group = tilesM < 16 ? tilesM : 16;
-    const unsigned long long per_group = group * tilesN;
-    const unsigned long long gidx = tid_in / per_group, r = tid_in % per_group;
-    const unsigned long long tile_m = gidx * group + (r % group), tile_n = r / group;
-    const unsigned long long Ksplit = (1ull << k) >> ks;
-    const int KT = (int)(Ksplit / TK);
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            mbar_init(&full[s], 1);         // the producer's expect_tx arrive + STAGE_BYTES of transactions
-            mbar_init(&empty[s], WM * WN);  // one arrive per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    for (int i = tid; i < TM; i += NC + 32) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
-    for (int i = tid; i < TN; i += NC + 32) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
-    __syncthreads();
-
-    if (warp >= WM * WN) {
-        // ===================== producer: one elected thread =====================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_a) : "memory");
-            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_b) : "memory");
-            const int k0 = (int)(split * Ksplit);
-            const int row_a = (int)(tile_m << TM_LOG2), row_b = (int)(tile_n << TN_LOG2);
-            for (int kt = 0; kt < KT; kt++) {
-                const int s = kt % STAGES;
-                if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);  // consumers released this slot
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(As + s * TM * TK, &map_a, k0 + kt * TK, row_a, &full[s]);
-                tma_load_2d(Bs + s * TN * TK, &map_b, k0 + kt * TK, row_b, &full[s]);
-            }
-        }
-        return;
-    }
-
-    // ===================== consumer warps =====================
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp % WM, wn = warp / WM;
-    double acc[MB][NB][2];
-#pragma unroll
-    for (int i = 0; i < MB; i++)
-#pragma unroll
-        for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int frag_off_a = (wm * WTM + g) * TK;
-    const int frag_off_b = (wn * WTN + g) * TK;
-    int koff[K4];  // column (doubles) of fragment element (k4, t) inside a swizzled 128-byte tile row of row & 7 == g
-#pragma unroll
-    for (int k4 = 0; k4 < K4; k4++) koff[k4] = (((k4 + 4 * (t >> 1)) ^ g) << 1) + (t & 1);
-    double af[2][MB], bf[2][NB];
-    for (int kt = 0; kt < KT; kt++) {
-        const int s = kt % STAGES;
-        mbar_wait(&full[s], (kt / STAGES) & 1);
-        const double* as = As + s * TM * TK + frag_off_a;
-        const double* bs = Bs + s * TN * TK + frag_off_b;
-#pragma unroll
-        for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * TK + koff[0]];
-#pragma unroll
-        for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * TK + koff[0]];
-#pragma unroll
-        for (int k4 = 0; k4 < K4; k4++) {
-            const int cur = k4 & 1, nxt = cur ^ 1;
-            if (k4 + 1 < K4) {
-#pragma unroll
-                for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * TK + koff[(k4 + 1) % K4]];
-#pragma unroll
-                for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * TK + koff[(k4 + 1) % K4]];
-            }
-#pragma unroll
-            for (int i = 0; i < MB; i++)
-#pragma unroll
-                for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
-        }
-        __syncwarp();                       // every lane's fragment loads of this stage have been consumed
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (EXACT && ((kt + 1) % (128 / TK) == 0 || kt + 1 == KT)) {
-#pragma unroll
-            for (int i = 0; i < MB; i++)
-#pragma unroll
-                for (int j = 0; j < NB; j++) {
-                    acc[i][j][0] = mod_reduce(acc[i][j][0], p.modp, p.inv_modp);
-                    acc[i][j][1] = mod_reduce(acc[i][j][1], p.modp, p.inv_modp);
-                }
-        }
-    }
-
-    // ---- epilogue (identical to k_gemm_dmma) ----
-    double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
-    const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
-    const bool vec = (p.mask_n & 1ull) != 0;
-#pragma unroll
-    for (int i = 0; i < MB; i++) {
-        const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < NB; j++) {
-            const int col = wn * WTN + j * 8 + 2 * t;
-            if (vec) {
-                *reinterpret_cast<double2*>(Cout + (rbase | cN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
-            } else {
-                Cout[rbase | cN[col]] = acc[i][j][0];
-                Cout[rbase | cN[col + 1]] = acc[i][j][1];
-            }
-        }
-    }
-}
-
-template <int TM_LOG2, int TN_LOG2, int STAGES>
-constexpr size_t gemm_tma_smem_bytes() {
-    return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * 16 * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16 + 1024;
-}
-
-// K-contiguous operand [rows x 2^k] as a 2-D tensor map with a (16 x box_rows) box and the 128-byte swizzle
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        cudaGetLastError();
-        return (EncodeTiledFn)f;
-    }();
-    return fn;
-}
-static bool make_operand_map(CUtensorMap* map, const double* base, int rows_log2, int k, int box_rows) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn || k > 31 || rows_log2 > 31) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)1 << k, (cuuint64_t)1 << rows_log2};
-    const cuuint64_t gstride[1] = {((cuuint64_t)8) << k};
-    const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1u, 1u};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int TM_LOG2, int TN_LOG2, int STAGES, bool SWZ = false>
 constexpr size_t gemm_ws_smem_bytes() {
     return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (SWZ ? 16 : 20) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16;
@@ -1031,8 +853,6 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_X k_gemm_dmma<7, 6, 4, 2, 16, 3, 2, true>
 #define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
 #define GEMM_76_WZ2_X k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2, true>
-#define GEMM_76_TMA k_gemm_dmma_tma<7, 6, 4, 2, 4, 2>
-#define GEMM_76_TMA_X k_gemm_dmma_tma<7, 6, 4, 2, 4, 2, true>
 
 template <int NT, int FWD>
 __global__ void k_microtree(const MicroOpDev* __restrict__ ops, const int32_t* __restrict__ cta_start, const double* leaves,
@@ -1055,10 +875,6 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_66_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ2_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_TMA, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tma_smem_bytes<7, 6, 4>());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_TMA_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_tma_smem_bytes<7, 6, 4>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_microtree<256, kMicroFwdMax>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kMicroDescBytes + (int)((kMicroLeafCache + 2 * kMicroFwdMax) * sizeof(double)));
@@ -1323,14 +1139,8 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
         if (p.modp > 0.0) {
             // exact mode: residue-arithmetic instantiations of the default kernels
-            if (op.tm_log2 == 7 && op.tn_log2 == 6 && (op.k - op.ksplit_log2) >= 8) {
-                CUtensorMap ma, mb;
-                if (tuning().gemm_feed == 1 && p.a_leaf < 0 && p.b_leaf < 0 && make_operand_map(&ma, p.a, op.m, op.k, 128) &&
-                    make_operand_map(&mb, p.b, op.n, op.k, 64))
-                    GEMM_76_TMA_X<<<(unsigned)blocks, 288, gemm_tma_smem_bytes<7, 6, 4>(), stream>>>(ma, mb, p);
-                else
-                    GEMM_76_WZ2_X<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            }
+            if (op.tm_log2 == 7 && op.tn_log2 == 6 && (op.k - op.ksplit_log2) >= 8)
+                GEMM_76_WZ2_X<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
             else if (op.tm_log2 == 7 && op.tn_log2 == 6)
                 GEMM_76_X<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
             else if (op.tm_log2 == 6 && op.tn_log2 == 6)
@@ -1345,17 +1155,10 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 // (a shared-memory-staged epilogue writing 512-byte runs was measured in round 2 and is 25-30 % SLOWER than
                 // the direct 16-byte scatter: profiles/r02b_kernel_lab_tma_staged.md — its barriers serialise the tile)
                 GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
-            else if (kk >= 8) {
-                // warp-specialised pipeline, 4-stage ring, mbarrier full/empty stages.  Feed: tensor-map copies from one
-                // elected thread (gemm_feed = 1) or LDGSTS from two producer warps (0); operands that carry a per-slice
-                // leaf offset (never the case for joins of this size in practice) stay on LDGSTS.
-                CUtensorMap ma, mb;
-                if (T.gemm_feed == 1 && p.a_leaf < 0 && p.b_leaf < 0 && make_operand_map(&ma, p.a, op.m + 0, op.k, 128) &&
-                    make_operand_map(&mb, p.b, op.n, op.k, 64))
-                    GEMM_76_TMA<<<(unsigned)blocks, 288, gemm_tma_smem_bytes<7, 6, 4>(), stream>>>(ma, mb, p);
-                else
-                    GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            }
+            else if (kk >= 8)
+                // warp-specialised pipeline, TWO producer warps issuing LDGSTS into a swizzled 4-stage ring, mbarrier
+                // full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
+                GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
             else if (kk >= 6)  // K = 64, 128: the shorter 3-stage ring fills faster
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else

@@ -13,7 +13,6 @@ echo "launch list rc=$?"
 timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma -s 2 -c 1 -o gpurun_out/gemm_14_13_10 -f python tools/one_join.py 14 13 10 > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm rc=$?"
 timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma -s 2 -c 1 -o gpurun_out/gemm_11_11_12 -f python tools/one_join.py 11 11 12 >> gpurun_out/ncu_gemm.log 2>&1
-timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma_tma -s 2 -c 1 -o gpurun_out/gemm_11_11_12_tma -f python tools/one_join.py 11 11 12 gemm_feed=1 >> gpurun_out/ncu_gemm.log 2>&1
 timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma_p -s 2 -c 1 -o gpurun_out/gemm_14_14_4 -f python tools/one_join.py 14 14 4 >> gpurun_out/ncu_gemm.log 2>&1
 timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma -s 2 -c 1 -o gpurun_out/gemm_11_10_10 -f python tools/one_join.py 11 10 10 >> gpurun_out/ncu_gemm.log 2>&1
 echo "captures done"; ls -la gpurun_out/*.ncu-rep
