@@ -92,10 +92,21 @@ def test_forced_generic_policy_and_gemm_selection():
     auto = CompiledPlan(flat).describe()
     kinds = [op["kind"] for op in auto["slice_ops"]]
     assert 1 in kinds, "the dominant joins of n=150 must go to the DMMA GEMM kernel"
+    import ctypes
+
+    from tensororder_b200 import cabi
+
+    def tuned(key):
+        v = ctypes.c_double()
+        assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0
+        return int(v.value)
+
     for op in auto["slice_ops"]:
-        if op["kind"] == 1:
-            assert op["m"] >= op["n"] >= 6 and (op["k"] >= 4 or (op["k"] >= 1 and op["m"] + op["n"] >= 18))
-            assert op["k"] - op["ksplit_log2"] >= 7 or op["ksplit_log2"] == 0
+        if op["kind"] == 1:  # what the measured dispatch table (csrc/tob_dispatch_table.h) allows on the GEMM kernel
+            min_free = tuned("gemm_min_free") if op["k"] >= tuned("gemm_min_k") else tuned("gemm_smallk_min_free")
+            assert op["m"] >= op["n"] >= min_free and op["k"] >= 1
+            assert op["m"] + op["n"] >= tuned("gemm_min_out.%d" % min(op["k"], 16))
+            assert op["k"] - op["ksplit_log2"] >= tuned("min_k_per_split_log2") or op["ksplit_log2"] == 0
     forced = CompiledPlan(flat, kernel_policy=1).describe()
     assert all(op["kind"] in (0, 2, 3) for op in forced["slice_ops"])
 

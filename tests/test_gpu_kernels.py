@@ -122,10 +122,11 @@ def tuning():
     saved = {}
 
     def set_(key, value):
-        if key not in saved:
-            v = ctypes.c_double()
-            assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0, cabi.last_error()
-            saved[key] = v.value
+        for one in (["gemm_min_out.%d" % k for k in range(1, 17)] if key == "gemm_min_out" else [key]):  # "gemm_min_out": every k
+            if one not in saved:
+                v = ctypes.c_double()
+                assert cabi.lib.tob_tuning_get(one.encode(), ctypes.byref(v)) == 0, cabi.last_error()
+                saved[one] = v.value
         assert cabi.lib.tob_tuning_set(key.encode(), float(value)) == 0, cabi.last_error()
 
     yield set_

@@ -305,3 +305,45 @@ def test_gpu_b200_mem_slicer_contracts_within_the_budget(ref):
         got = float(api.contract_sliced(plan))
         assert api.last_stats["peak_bytes"] <= budget
         assert abs(got - want) <= 1e-9 * want, (name, got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("entry_type", ["int", "uint", "float32", "float16", "bigint"])
+def test_gpu_entry_types_match_the_reference_numpy_backend(ref, entry_type):
+    """The reference's dtype table (numpy_apis.py:15-22) on the same live plan objects: int / uint wrap modulo 2^64
+    exactly like numpy's integer tensordot (n=150 has 2.3e28 covers: several wraps), float32 / float16 within the
+    tolerances stated in B200API's docstring, bigint equal as Python ints."""
+    import numpy as np
+    import tensor_network
+
+    from conftest import load_golden
+    from tensororder_b200.api import B200API
+
+    cases = [("vc50_lineflow", None), ("vc50_lineflow", "min3"), ("vc100_lineflow", None)]
+    if entry_type in ("int", "uint", "float32"):
+        cases.append(("vc150_lineflow", "min4"))
+    if entry_type in ("float32", "float16"):
+        cases.append(("vc50_mcc_lineflow", None))  # weighted: the leaves themselves are rounded to the entry type
+    for name, variant in cases:
+        pp = load_golden(name)
+        pp = pp.variant(variant) if variant else pp
+        plan = reference.to_reference_plan(ref, pp, as_int=(entry_type == "bigint"))
+        theirs = tensor_network.ALL_APIS["numpy"]()
+        theirs.add_argument("entry_type", entry_type)
+        ours = B200API()
+        ours.add_argument("entry_type", entry_type)
+        with np.errstate(over="ignore"):
+            want = theirs.contract_sliced(plan)
+        got = ours.contract_sliced(plan)
+        if entry_type in ("int", "uint"):
+            assert int(got) == int(want), (name, variant, got, want)
+            assert type(got) is type(want)
+        elif entry_type == "bigint":
+            assert isinstance(got, int) and got == int(want), (name, variant)
+        else:
+            tol = 5e-6 if entry_type == "float32" else 5e-3
+            if np.isfinite(want):
+                assert abs(float(got) - float(want)) <= tol * abs(float(want)), (name, variant, got, want)
+                assert type(got) is type(want)
+            else:  # beyond the entry type's range the reference overflows; so does the rounded float64 result
+                assert not np.isfinite(got) or abs(float(got)) > 6e4

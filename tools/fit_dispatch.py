@@ -5,8 +5,8 @@ under `tob_tuning_set` overrides and derives
   A. the split-K time model's constants (alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us): every power-of-two
      split of a grid of GEMM shapes is timed, the constants are fitted to the measured times (least squares on
      log(model / measured)), and the table prints the split the fitted model picks next to the measured best;
-  B. the generic <-> DMMA GEMM crossover (gemm_min_total for k >= 4, gemm_smallk_min_out for 1 <= k <= 3);
-  C. the generic kernel classes (t1_max_k, t32_max_k) and the persistent short-K range (persist_max_k).
+  B. the generic <-> DMMA GEMM crossover as a table by k (gemm_min_out[k]: the smallest m + n from which the GEMM wins);
+  C. the generic kernel classes (t1_max_k, t1_small_*, t32_max_k) and the persistent short-K range (persist_max_k).
 
 Usage (GPU box):  python tools/fit_dispatch.py [--quick]
 Writes gpurun_out/dispatch_fit.json (raw measurements) and gpurun_out/tob_dispatch_table.h (copy it over
@@ -253,7 +253,7 @@ src = open(os.path.join(REPO, "tensororder_b200", "csrc", "tob_dispatch_table.h"
 lines = []
 for ln in src:
     if ln.startswith("// generated:"):
-        ln = "// generated: %s on %s by tools/fit_dispatch.py (fit rms log error %.3f over %d timings; raw: profiles/r02_dispatch_fit.json)" % (
+        ln = "// generated: %s on %s by tools/fit_dispatch.py (fit rms log error %.3f over %d timings; raw: profiles/r02e_dispatch_fit.json)" % (
             out["when"], out["gpu"], out["fit"]["rms_log_error"], len(rows))
     if ln.startswith("#define TOB_TUNE_"):
         name = ln.split()[1][len("TOB_TUNE_"):]

@@ -34,7 +34,7 @@ for T in Ts:
         a = torch.rand(1 << ra, dtype=torch.float64, device="cuda")
         b = torch.rand(1 << rb, dtype=torch.float64, device="cuda")
         c = torch.empty(1 << rc, dtype=torch.float64, device="cuda")
-        ws_bytes = 8 * ((1 << ra) + (1 << rb) + min(1 << (rc + 4), 1 << 28)) + 4096
+        ws_bytes = 8 * ((1 << ra) + (1 << rb) + min(1 << (rc + 8), 1 << 28)) + 4096  # permuted operands + split-K partials (up to 2^8 splits)
         ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device="cuda")
         rng = np.random.default_rng(1000 * T + k)
         for placement in ("ready", "random"):
