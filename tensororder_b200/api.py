@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import dataclasses
+import threading
 import time
 from collections import OrderedDict
 from ctypes import byref, c_double, c_float, c_int32, c_void_p
@@ -73,6 +74,7 @@ class CompiledPlan:
                  slice_lanes: int = 0, dag_branches: int = 0):
         self.flat = flat
         self._handle = c_void_p()
+        self.busy = 0  # plan cache: a call is running on this plan (another host thread must not share or evict it)
         self.interruptible_stats = {"device_ms": 0.0, "launches": 0, "gemm": (0.0, 0.0, 0)}
         desc = cabi.tob_plan_desc()
         desc.n_nodes = flat.n_nodes
@@ -262,6 +264,15 @@ class CompiledPlan:
             pass
 
 
+def _locked(method):
+    def wrapper(self, *args, **kwargs):
+        with self.lock:
+            return method(self, *args, **kwargs)
+
+    wrapper.__name__, wrapper.__doc__ = method.__name__, method.__doc__
+    return wrapper
+
+
 class PlanCache:
     """Compiled plans keyed by plan identity (SURVEY.md §8b "Ownership": the backend owns all device memory
     and must release it per call or cache it keyed by plan identity).
@@ -281,39 +292,54 @@ class PlanCache:
     def __init__(self):
         self.entries = OrderedDict()
         self.hits = self.misses = 0
+        self.lock = threading.RLock()  # several host threads may contract independent plans through B200API at once
 
     @staticmethod
     def key(plan, options):
         groups = tuple(tuple(sorted(int(e) for e in g)) for g in plan.groups_to_slice)
         return (id(plan.tree), id(plan.network), groups, options)
 
+    @_locked
     def lookup(self, plan, options):
         k = self.key(plan, options)
         e = self.entries.get(k)
-        if e is not None and e["tree"] is plan.tree and e["network"] is plan.network:
+        if e is not None and e["tree"] is plan.tree and e["network"] is plan.network and e["compiled"].busy == 0:
             self.entries.move_to_end(k)
             self.hits += 1
+            e["compiled"].busy += 1
             return e
         self.misses += 1
         return None
 
+    @_locked
     def store(self, plan, options, compiled):
         k = self.key(plan, options)
-        old = self.entries.pop(k, None)
+        old = self.entries.get(k)
+        if old is not None and old["compiled"].busy > 0:
+            return False  # another thread is running this very plan: the caller keeps a private, uncached copy
         if old is not None and old["compiled"] is not compiled:
-            old["compiled"].close()
+            self.entries.pop(k)["compiled"].close()
+        compiled.busy += 1
         self.entries[k] = {"tree": plan.tree, "network": plan.network, "compiled": compiled}
-        while len(self.entries) > self.MAX_ENTRIES:
-            _, e = self.entries.popitem(last=False)
-            e["compiled"].close()
+        for old_key in [q for q, e in self.entries.items() if e["compiled"].busy == 0][: max(0, len(self.entries) - self.MAX_ENTRIES)]:
+            self.entries.pop(old_key)["compiled"].close()
+        return True
 
+    @_locked
     def drop(self, plan, options):
         e = self.entries.pop(self.key(plan, options), None)
         if e is not None:
             e["compiled"].close()
 
+    @_locked
+    def failed(self, compiled):
+        compiled.busy = max(0, compiled.busy - 1)
+        compiled.release_device()
+
+    @_locked
     def after_call(self, compiled):
         """Residency policy: big arenas go back to the pool at once, small ones stay (LRU within the budget)."""
+        compiled.busy = max(0, compiled.busy - 1)
         if not compiled.uploaded:
             return
         if compiled.peak_bytes > self.RESIDENT_PLAN_BYTES:
@@ -325,9 +351,10 @@ class PlanCache:
             if not c.uploaded:
                 continue
             total += c.peak_bytes
-            if total > self.RESIDENT_TOTAL_BYTES and c is not compiled:
+            if total > self.RESIDENT_TOTAL_BYTES and c is not compiled and c.busy == 0:
                 c.release_device()
 
+    @_locked
     def clear(self):
         for e in self.entries.values():
             e["compiled"].close()
@@ -454,7 +481,9 @@ class B200API:
                 data = rebuild_leaf_data(execution_plan, compiled.flat)
                 if data is not None:
                     compiled.flat = dataclasses.replace(compiled.flat, leaf_data=self._cast_leaves(np.ascontiguousarray(data)))
+                    compiled.cached = True
                     return compiled, True
+                compiled.busy = 0
                 PLAN_CACHE.drop(execution_plan, options)
         flat = flatten_plan(execution_plan)  # leaves are built through a buffer-backed create_tensor
         flat = dataclasses.replace(flat, leaf_data=self._cast_leaves(flat.leaf_data))
@@ -462,15 +491,14 @@ class B200API:
                                 kernel_policy=self._kernel_policy, hoist_invariant=self._hoist,
                                 use_microtree=self._microtree, slice_lanes=self._lanes,
                                 dag_branches=self._branches, mem_limit_bytes=self._mem_limit_bytes)
-        if self._plan_cache:
-            PLAN_CACHE.store(execution_plan, options, compiled)
+        compiled.cached = bool(self._plan_cache and PLAN_CACHE.store(execution_plan, options, compiled))
         return compiled, False
 
     def _done_with(self, compiled, failed=False):
-        if not self._plan_cache:
+        if not getattr(compiled, "cached", True):
             compiled.close()
         elif failed:
-            compiled.release_device()
+            PLAN_CACHE.failed(compiled)
         else:
             PLAN_CACHE.after_call(compiled)
 

@@ -158,3 +158,22 @@ def test_exact_mode_with_mixed_signs_uses_the_a_priori_bound(fake):
     sliced = load_golden("vc50_lineflow").variant("min3")
     sliced.tensors = pp.tensors
     assert _api("bigint").contract_sliced(sliced.as_execution_plan()) == got  # slicing-invariant
+
+
+def test_plan_cache_with_two_host_threads(fake):
+    """Independent plans (and even the same plan object) contracted from two host threads through the public call:
+    a cached plan that is running is neither shared nor evicted."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    a = load_golden("vc50_lineflow").as_execution_plan()
+    b = load_golden("vc50_mcc_lineflow").as_execution_plan()
+    want_b = load_golden("vc50_mcc_lineflow").expected["count"]
+
+    def many(plan, n):
+        return [float(_api().contract_sliced(plan)) for _ in range(n)]
+
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        fa, fb, fa2 = pool.submit(many, a, 6), pool.submit(many, b, 6), pool.submit(many, a, 6)
+        assert all(v == 2802717837.0 for v in fa.result() + fa2.result())
+        assert all(v == pytest.approx(want_b, rel=1e-12) for v in fb.result())
+    assert all(e["compiled"].busy == 0 for e in PLAN_CACHE.entries.values())
