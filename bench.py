@@ -411,7 +411,7 @@ def extra_rank_sweep(torch, dev, hbm_gbs, fp64_peak):
         a = torch.rand(1 << ra, dtype=torch.float64, device=dev)
         b = torch.rand(1 << rb, dtype=torch.float64, device=dev)
         c = torch.empty(1 << rc, dtype=torch.float64, device=dev)
-        ws_bytes = 8 * min(1 << (rc + 6), 1 << 28) + 4096
+        ws_bytes = 8 * min(1 << (rc + 8), 1 << 28) + 4096  # split-K partials up to 2^8 splits
         ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
         aa = np.arange(ra - k, ra, dtype=np.int32)
         ab = np.arange(rb - k, rb, dtype=np.int32)

@@ -347,3 +347,22 @@ def test_gpu_entry_types_match_the_reference_numpy_backend(ref, entry_type):
                 assert type(got) is type(want)
             else:  # beyond the entry type's range the reference overflows; so does the rounded float64 result
                 assert not np.isfinite(got) or abs(float(got)) > 6e4
+
+
+@pytest.mark.gpu
+def test_gpu_cli_under_torchrun_two_gpus(ref, tmp_path):
+    """`torchrun --nproc-per-node 2 -m tensororder_b200.launch src/execution.py --tensor_library=b200 < N.con`: one
+    process per GPU, slices r::2, one NCCL all-reduce; rank 0 prints the same count as the reference's numpy run."""
+    from tensororder_b200 import cabi
+
+    if cabi.lib.tob_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    con = _con_bytes(ref, "vc150_lineflow", tmp_path)
+    out_n, _, _ = _cli("execution.py", ["--rank_limit=19"], con, library="numpy")
+    out_b, err_b, rc = _cli("execution.py", ["--rank_limit=19"], con, library="b200", torchrun=2)
+    assert rc == 0, err_b[-2000:]
+    assert out_b.count("Count:") == 1
+    cb, cn = float(_field(out_b, "Count")), float(_field(out_n, "Count"))
+    assert abs(cb - cn) <= 1e-9 * abs(cn)
+    assert int(_field(out_b, "# Network Slices")) >= 2 and float(_field(out_b, "Contraction Time")) > 0
+    print("2 GPUs: Count %r, Contraction Time %s s (numpy, one process: %s s)" % (cb, _field(out_b, "Contraction Time"), _field(out_n, "Contraction Time")))

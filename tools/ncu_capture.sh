@@ -1,14 +1,15 @@
 #!/bin/bash
 # ncu evidence for the round (run on the GPU box, one GPU):  bash tools/ncu_capture.sh
-#  1. launch list of a short bench run (per-launch device times: compare SHARES with the bench line, not absolutes)
+#  1. launch list of ONE sequential pass over the bench workload, plain stream launches (tools/one_pass.py; per-launch
+#     device times are cold-cache and serialised: compare SHARES with the bench line, not absolutes)
 #  2. `--set full` captures of the dominant GEMM class (m=14,n=13,k=10: the join profiles/gemm_traffic.json names),
-#     a ~1 ms GEMM of the sliced plans (m=11,n=11,k=12) with both operand feeds, and a store-bound join (k=4).
+#     a ~1 ms GEMM of the sliced plans (m=11,n=11,k=12), a store-bound join (k=4) and config 3's dominant join (m=11,n=10,k=10).
 # Outputs land in gpurun_out/; tools/ncu_summary.py turns the .ncu-rep files into the JSON summaries under profiles/.
 set -u
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
-timeout 400 $NCU --metrics gpu__time_duration.sum -c 6000 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-extra --no-large --no-cpu-baseline --e2e-steps 1 > gpurun_out/launches_bench.json 2> gpurun_out/launches_bench.err
+timeout 500 $NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file gpurun_out/launches.csv \
+    python tools/one_pass.py 1 > gpurun_out/launches_pass.log 2>&1
 echo "launch list rc=$?"
 timeout 200 $NCU --set full --import-source on -k regex:k_gemm_dmma -s 2 -c 1 -o gpurun_out/gemm_14_13_10 -f python tools/one_join.py 14 13 10 > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm rc=$?"
