@@ -3,8 +3,8 @@
 
 Rebuilds reference objects from a portable plan — `TensorNetwork` (+`BuiltTensor` leaves, edges
 connected in edge-id order), `ContractionTreeContext.leaf/join`, `SlicedExecutionPlan` with the stored
-`groups_to_slice` — and calls `NumpyAPI.contract_sliced`.  Build container only (needs the scratch
-build of /root/reference made by make_golden.py).
+`groups_to_slice` (`oracle.reference.to_reference_plan`) — and calls `NumpyAPI.contract_sliced`.  Needs the reference
+built into oracle/_ref/ (`python -m oracle.reference`).
 
 Usage: python tests/golden/ref_replay.py NAME[:VARIANT] [...]      (writes expected.count into the fixture)
        python tests/golden/ref_replay.py --bigint NAME[:VARIANT] [...]   (reference `--entry_type=bigint`:
