@@ -51,6 +51,7 @@ METRIC = "contraction s/instance (plan excluded)"
 UNIT = "s/instance"
 FP64_CUBLAS_CALIBRATION = 35.49  # cuBLAS DGEMM 8192^3 on this pool's B200s, round 1 (profiles/r01_fp64_calibration.txt)
 FP64_DMMA_PIPE = 37.1            # raw DMMA.8x8x4 issue peak measured by tools/fp64_peak.cu (same file)
+E2E_THREADS = 4                   # host threads of the e2e arm at N = 1: the three sliced instances and the small ones
 
 
 def measured_peaks():
@@ -425,16 +426,45 @@ def extra_rank_sweep(torch, dev, hbm_gbs, fp64_peak):
                 raise RuntimeError(cabi.last_error())
             if rep and (best is None or ms[1] < best):
                 best = ms[1]
+        # the same launch back to back (R launches captured into one CUDA graph): a join inside a tree follows its
+        # predecessor on the stream, without the ~5 us a lone event-bracketed launch carries
+        reps = 20 if T <= 30 else 4
+        side = torch.cuda.Stream(device=dev)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(reps):
+                rc_ = cabi.lib.tob_tensordot_device(a.data_ptr(), ra, b.data_ptr(), rb, aa.ctypes.data_as(P32),
+                                                    ab.ctypes.data_as(P32), k, c.data_ptr(), ws.data_ptr(), ws_bytes, 0,
+                                                    ctypes.c_void_p(side.cuda_stream), None)
+                if rc_ != 0:
+                    raise RuntimeError(cabi.last_error())
+        b2b = None
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1) / reps
+            b2b = t if b2b is None or t < b2b else b2b
+        del graph
         flops = 2.0 * 2.0 ** T
         byts = 8.0 * (2.0 ** ra + 2.0 ** rb + 2.0 ** rc)
         tf = flops / (best * 1e-3) / 1e12
         gb = byts / (best * 1e-3) / 1e9
         bound = "tensor" if flops / (fp64_peak * 1e12) > byts / (hbm_gbs * 1e9) else "hbm"
+        work, peak = (flops / 1e12, fp64_peak) if bound == "tensor" else (byts / 1e9, hbm_gbs)
         rows.append({"T": T, "k": k, "ms": best, "tflops": tf, "gbs": gb, "bound": bound,
-                     "frac": tf / fp64_peak if bound == "tensor" else gb / hbm_gbs})
+                     "frac": tf / fp64_peak if bound == "tensor" else gb / hbm_gbs,
+                     "ms_back_to_back": b2b, "frac_back_to_back": work / (b2b * 1e-3) / peak})
         del a, b, c, ws
         torch.cuda.empty_cache()
     return {"config": "BASELINE config 5 digest: single contractions, T total / k contracted indices, GEMM-ready operands",
+            "timing": "ms / frac: ONE launch between two CUDA events (best of 3); ms_back_to_back / frac_back_to_back: the same "
+                      "launch repeated inside one CUDA graph, replay time / repetitions (operands of T <= 30 stay in the 126 MB L2 "
+                      "either way, as they do behind their producer in a tree)",
             "points": rows}
 
 
@@ -604,20 +634,30 @@ def b200_arm(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         return [contract_one(it) for it in batch]
 
-    shared_items = [it for it in mine if it["owner"] is None or world == 1 and it["nsl"] > 1]
-    solo_items = [it for it in mine if it not in shared_items]
-    pool = ThreadPoolExecutor(max_workers=1)
+    # host threads making the public call: the instances of a step are independent objects, so a user contracts them from
+    # a small thread pool (ctypes releases the GIL inside the C ABI; every plan runs on its own streams, so the GPU sees
+    # several contractions at once and one thread's host work hides behind another's device time).  N > 1: the sliced
+    # instances stay on ONE thread — each call ends in an all-reduce that must be issued in the same order on every rank —
+    # and the rank's unsliced instances go to a second one.  N = 1: no collective, four threads (longest-first packing: one per sliced instance, one for the small ones).
+    if world > 1:
+        groups = [[it for it in mine if it["owner"] is None], [it for it in mine if it["owner"] is not None]]
+    else:
+        groups, gload = [[] for _ in range(E2E_THREADS)], [0.0] * E2E_THREADS
+        for it in sorted(mine, key=lambda x: -x["model_s"]):
+            g = min(range(E2E_THREADS), key=lambda q: gload[q])
+            groups[g].append(it)
+            gload[g] += it["model_s"]
+    groups = [g for g in groups if g] or [[]]
+    pool = ThreadPoolExecutor(max_workers=max(1, len(groups) - 1))
     for step in range(1 + e2e_steps):  # one warm-up pass (pays the plan compiles: cached by plan identity afterwards)
         barrier()
         t0 = time.perf_counter()
         host = np.zeros(n_inst)
         h2d = d2h = 0
-        # the rank's unsliced instances are independent objects: a second host thread contracts them through the same
-        # public call (ctypes releases the GIL inside the C ABI) while this thread contracts the sliced ones, whose
-        # all-reduces must be issued in the same order on every rank
-        side = pool.submit(contract_unsliced, solo_items)
-        results = [(it, contract_one(it)) for it in shared_items]
-        results += list(zip(solo_items, side.result()))
+        side = [pool.submit(contract_unsliced, g) for g in groups[1:]]
+        results = [(it, contract_one(it)) for it in groups[0]]
+        for g, fut in zip(groups[1:], side):
+            results += list(zip(g, fut.result()))
         for it, (got, stats) in results:
             host[index[it["name"]]] = got
             h2d += stats["h2d_bytes"]
@@ -667,7 +707,7 @@ def b200_arm(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
-                    "step_seconds": e2e_step_s, "plan_cache_hits_rank0": cache_hits, "host_threads": 2,
+                    "step_seconds": e2e_step_s, "plan_cache_hits_rank0": cache_hits, "host_threads": len(groups),
                     "rank0_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(lt.item()), "clocks": clocks, "counts_ok": ok, "instances": n_inst,
             "issue": "sequential" if args.sequential else "async: all of a rank's instances in flight",

@@ -60,6 +60,12 @@ Tuning& tuning() {
         x.max_ksplit_log2 = TOB_TUNE_MAX_KSPLIT_LOG2;
         x.min_k_per_split_log2 = TOB_TUNE_MIN_K_PER_SPLIT_LOG2;
         x.force_ksplit_log2 = -1;
+        x.streamk = TOB_TUNE_STREAMK;
+        x.streamk_min_tiles_log2 = TOB_TUNE_STREAMK_MIN_TILES_LOG2;
+        x.streamk_max_tiles_log2 = TOB_TUNE_STREAMK_MAX_TILES_LOG2;
+        x.store_bulk = TOB_TUNE_STORE_BULK;
+        x.streamk_fix_us = TOB_TUNE_STREAMK_FIX_US;
+        x.store_group_log2 = TOB_TUNE_STORE_GROUP_LOG2;
         return x;
     }();
     return t;
@@ -79,6 +85,9 @@ const TuneField kTuneFields[] = {
     {"reduce_gbs", nullptr, &Tuning::reduce_gbs}, {"reduce_fix_us", nullptr, &Tuning::reduce_fix_us},
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
+    {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
+    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"store_bulk", &Tuning::store_bulk, nullptr},
+    {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };
 // "gemm_min_out" sets every k at once, "gemm_min_out.<k>" one entry
 int min_out_index(const char* key) {
@@ -134,12 +143,35 @@ double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c) 
     return t;
 }
 
+// Stream-K: every CTA slot carries the same number of K steps (ceil(tiles * KT / slots)), whatever the tile count; the
+// price is one partial 128x64 tile written and read per CTA plus the owners' waits (streamk_fix_us, fitted).  Eligible:
+// 128x64 tiles, K >= 256 (the warp-specialised pipeline), 64..256 tiles: fewer and an owner sums too many partials (32
+// tiles: 9 each, measured 6 % slower than split-K); more and the one-tile-per-CTA grid is already balanced by the block
+// scheduler while stream-K ranges spread over the whole tile space lose the raster's L2 locality (512 tiles: 13-25 %
+// slower, 1024+: 25-40 % — profiles/r02h_kernel_lab_streamk.md).
+double streamk_time_model_us(int m, int n, int k, int* ctas) {
+    const Tuning& T = tuning();
+    if (m < 7 || n < 6 || k < 8) return -1.0;
+    const int tiles_log2 = (m - 7) + (n - 6);
+    if (tiles_log2 < T.streamk_min_tiles_log2 || tiles_log2 > T.streamk_max_tiles_log2 || tiles_log2 + (k - 4) > 40) return -1.0;
+    const double slots = 2.0 * kNumSMs;
+    if (slots > (kSkFlagBytes / 4 - 1)) return -1.0;
+    const double G = std::ldexp(1.0, tiles_log2 + k - 4), KT = std::ldexp(1.0, k - 4);
+    if (G < slots) return -1.0;
+    const double steps = std::ceil(G / slots);
+    if (steps / KT + 2.0 > kSkMaxSegs) return -1.0;
+    if (ctas) *ctas = (int)slots;
+    const double step_shared = 2.0 * std::ldexp(1.0, 7 + 6 + 4) / (T.sm_gflops * 1e3 / 2.0);
+    return steps * step_shared + T.gemm_fix_us + T.streamk_fix_us;
+}
+
 void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     const Tuning& T = tuning();
     const int m = op->m, n = op->n, k = op->k;
     op->flops = 2.0 * std::ldexp(1.0, m + n + k);
     op->bytes = 8.0 * (std::ldexp(1.0, m + k) + std::ldexp(1.0, n + k) + std::ldexp(1.0, m + n));
     op->ksplit_log2 = 0;
+    op->streamk = 0;
     // k >= gemm_min_k: the DMMA pipeline proper.  1 <= k < gemm_min_k with a large two-sided output (outer-product-
     // like joins): the same kernel with a zero-filled K step, i.e. a tiled store kernel with full operand reuse,
     // instead of one thread per output re-reading both rows from L2.  The crossover against the generic kernels is
@@ -160,6 +192,14 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
                 if (t < best * 0.97) { best = t; ks = c; }
             }
             if (T.force_ksplit_log2 >= 0) ks = std::max(0, std::min(T.force_ksplit_log2, k - 4));
+            if (T.streamk > 0 && op->tm_log2 == 7 && op->tn_log2 == 6) {
+                int ctas = 0;
+                const double t = streamk_time_model_us(m, n, k, &ctas);
+                if (t > 0.0 && (T.streamk >= 2 || (T.force_ksplit_log2 < 0 && t < best * 0.97))) {
+                    op->streamk = ctas;
+                    ks = 0;
+                }
+            }
         }
         op->ksplit_log2 = ks;
         return;
@@ -321,7 +361,7 @@ int schedule_branches(std::vector<Op>* list_p, int max_branches) {
             if (!(overlap && R.lo >= lo && R.hi <= hi)) recs[keep++] = R;  // fully overwritten records are superseded
         }
         recs.resize(keep);
-        if (op.ksplit_log2 > 0) {
+        if (op.ksplit_log2 > 0 || op.streamk > 0) {  // the lane's one workspace (and its stream-K flags)
             if (last_ws > barrier) deps.push_back(last_ws);
             last_ws = j;
         }
@@ -609,6 +649,10 @@ int compile(const tob_plan_desc* d, const tob_options* opt_in, Program* P, std::
             op.ws_offset = 0;
             ws_max = std::max(ws_max, round_up(size_of[i] << op.ksplit_log2, kAlign));
         }
+        if (op.streamk > 0) {
+            op.ws_offset = 0;
+            ws_max = std::max(ws_max, round_up((int64_t)op.streamk * kSkSlotDoubles, kAlign));
+        }
         for (int c : {X.left, X.right}) {
             const NodeInfo& Cn = P->nodes[c];
             if (Cn.leaf < 0 && !persistent[c]) arena.release(Cn.where.offset, size_of[c], i);
@@ -747,7 +791,7 @@ std::string describe(const Program& P) {
             ref(op.b);
             o << ",\"c_offset\":" << op.c_offset << ",\"m\":" << op.m << ",\"n\":" << op.n << ",\"k\":" << op.k
               << ",\"mask_m\":" << op.mask_m << ",\"threads_per_out\":" << op.threads_per_out
-              << ",\"ksplit_log2\":" << op.ksplit_log2 << ",\"tm_log2\":" << op.tm_log2 << ",\"tn_log2\":" << op.tn_log2
+              << ",\"ksplit_log2\":" << op.ksplit_log2 << ",\"streamk\":" << op.streamk << ",\"tm_log2\":" << op.tm_log2 << ",\"tn_log2\":" << op.tn_log2
               << ",\"invariant\":" << op.invariant << ",\"flops\":" << op.flops << ",\"bytes\":" << op.bytes
               << ",\"branch\":" << op.branch << ",\"signal\":" << op.signal << ",\"waits\":[";
             for (size_t w = 0; w < op.waits.size(); w++) o << (w ? "," : "") << op.waits[w];

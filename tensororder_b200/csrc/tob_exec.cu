@@ -38,6 +38,7 @@ struct Lane {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // lane 0: run start / end;  lane >= 1: fork / done
     double* d_arena = nullptr;
     double* d_ws = nullptr;
+    unsigned* d_sk_flags = nullptr;  // stream-K counter + flags (zeroed at upload, self-cleaning afterwards)
     long long* d_leaf_off = nullptr;
     DevState* d_state = nullptr;
     cudaGraph_t graph = nullptr;
@@ -536,6 +537,8 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         o_mops[w] = section(G.micro[w].ops.size() * sizeof(MicroOpDev) + 8);
         o_mstart[w] = section(G.micro[w].cta_start.size() * sizeof(int32_t) + 8);
     }
+    size_t o_skf[kMaxLanes];
+    for (int l = 0; l < NL; l++) o_skf[l] = section(kSkFlagBytes);  // inside the zero-initialised prefix
     const size_t o_leaves = section((size_t)G.leaf_doubles * 8);
     const size_t prefix_bytes = off;  // everything up to here is initialised from the pinned mirror
     size_t o_arena[kMaxLanes], o_ws[kMaxLanes];
@@ -569,6 +572,7 @@ int tob_plan_upload(tob_plan* p, const double* leaf_data, int64_t n_doubles) {
         p->lane[l].d_leaf_off = reinterpret_cast<long long*>(d + o_leaf_off[l]);
         p->lane[l].d_arena = reinterpret_cast<double*>(d + o_arena[l]);
         p->lane[l].d_ws = reinterpret_cast<double*>(d + o_ws[l]);
+        p->lane[l].d_sk_flags = reinterpret_cast<unsigned*>(d + o_skf[l]);
     }
     p->d_acc = reinterpret_cast<double*>(d + o_acc);
     p->d_results = reinterpret_cast<double*>(d + o_results);
@@ -693,6 +697,8 @@ static KParams make_params(const tob_plan* p, const Lane& L, const Op& op) {
     k.b = operand_ptr(p, L, op.b);
     k.c = L.d_arena + op.c_offset;
     k.ws = L.d_ws;
+    k.sk_flags = L.d_sk_flags;
+    k.streamk = op.streamk;
     k.leaf_off = L.d_leaf_off;
     k.a_leaf = op.a.leaf;
     k.b_leaf = op.b.leaf;
@@ -1209,12 +1215,17 @@ int tob_tensordot_device(const double* a, int32_t rank_a, const double* b, int32
         std::swap(op.m, op.n);
         op.mask_m = full & ~op.mask_m;
     }
+    const int64_t need_perm = need;   // what the operand permutations alone require
+    need = (need + 255) & ~(int64_t)255;
+    const int64_t off_flags = need;  // stream-K counter + flags, zeroed below when the join runs on that kernel
+    need += kSkFlagBytes;
     off_ws = need;
     const int64_t ws_avail = (workspace ? workspace_bytes : 0) - need;
     choose_kernel(&op, kernel_policy, true);
+    if (op.streamk > 0 && (int64_t)op.streamk * kSkSlotDoubles * 8 > ws_avail) op.streamk = 0;  // no room for the partial tiles: one tile per CTA
     while (op.ksplit_log2 > 0 && ((int64_t)8 << (op.m + op.n + op.ksplit_log2)) > ws_avail) op.ksplit_log2--;
-    if ((pa || pb) && (!workspace || workspace_bytes < need)) {
-        set_error("tensordot needs a workspace of at least " + std::to_string(need) + " bytes for the operand permutations");
+    if ((pa || pb) && (!workspace || workspace_bytes < need_perm)) {
+        set_error("tensordot needs a workspace of at least " + std::to_string(need_perm) + " bytes for the operand permutations");
         return TOB_E_INVALID;
     }
     EventSet es;
@@ -1249,6 +1260,11 @@ int tob_tensordot_device(const double* a, int32_t rank_a, const double* b, int32
     kp.a_leaf = kp.b_leaf = -1;
     kp.m = op.m; kp.n = op.n; kp.k = op.k;
     kp.ksplit_log2 = op.ksplit_log2;
+    kp.streamk = op.streamk;
+    if (op.streamk > 0) {
+        kp.sk_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + off_flags);
+        CUDA_TRY(cudaMemsetAsync(kp.sk_flags, 0, kSkFlagBytes, stream));
+    }
     kp.mask_m = op.mask_m;
     const int tot = op.m + op.n;
     kp.mask_n = tot == 0 ? 0ull : (~op.mask_m & (tot >= 64 ? ~0ull : ((1ull << tot) - 1ull)));

@@ -39,6 +39,8 @@ struct Op {
     // generic kernel configuration
     int32_t threads_per_out = 1;  // 1, 32 or 256
     int32_t ksplit_log2 = 0;      // K split across CTAs (partials in the workspace, reduced deterministically)
+    int32_t streamk = 0;          // > 0: stream-K GEMM on this many CTAs (the K steps of all tiles cut into equal ranges;
+                                  // partial tiles in the workspace, summed by the tile's owner in CTA order)
     // gemm kernel configuration
     int32_t tm_log2 = 7, tn_log2 = 7;
     int64_t ws_offset = -1;     // workspace offset (doubles) for split-K partials
@@ -115,6 +117,11 @@ void set_error(const std::string& msg);
 int num_sms();
 void set_num_sms(int n);
 
+// stream-K GEMM (k_gemm_dmma_sk): one partial 128x64 tile per CTA in the workspace, a 4 KB counter + flag block per lane
+constexpr int kSkFlagBytes = 4096;
+constexpr int64_t kSkSlotDoubles = 128 * 64;
+constexpr int kSkMaxSegs = 16;  // tiles a CTA's range may touch
+
 // Per-join dispatch parameters: defaults come from the measured table tob_dispatch_table.h (generated by
 // tools/fit_dispatch.py); tob_tuning_set overrides single values at run time (experiments, the fit itself).
 struct Tuning {
@@ -125,11 +132,19 @@ struct Tuning {
     double sm_gflops, alone_frac, gemm_fix_us, reduce_gbs, reduce_fix_us;
     int max_ksplit_log2, min_k_per_split_log2;
     int force_ksplit_log2;  // >= 0: experiments only — every split-capable GEMM uses this split
+    int streamk;            // 0: never, 1: where the time model says so, 2: experiments only — every eligible GEMM
+    int streamk_min_tiles_log2;  // stream-K needs at least this many tiles (few tiles => many partials per owner)
+    int streamk_max_tiles_log2;  // ... and at most this many (ranges over several tiles lose the L2 locality of the raster)
+    double streamk_fix_us;  // modelled cost of the partial-tile exchange
+    int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
+    int store_bulk;         // persistent short-K kernel: 1 = tiles leave through shared memory as bulk (TMA) stores
 };
 Tuning& tuning();
 bool tuning_set(const char* key, double value);
 bool tuning_get(const char* key, double* value);
 // Modelled duration (microseconds) of a GEMM-kernel join with K split 2^c ways (choose_kernel minimises it).
 double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c);
+// Modelled duration of the same join on the stream-K kernel; `ctas` receives its grid.  < 0: not eligible.
+double streamk_time_model_us(int m, int n, int k, int* ctas);
 
 }  // namespace tob

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma(KParams p) {
     constexpr int RPP = NT / CHUNKS;             // rows per loader pass
     constexpr int K4 = TK / 4;
     static_assert(TM % RPP == 0 && TN % RPP == 0, "loader passes");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + STAGES * TM * LDS;
     unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
     constexpr int RPP = NT / CHUNKS;
     constexpr int K4 = TK / 4;
     static_assert(TM % RPP == 0 && TN % RPP == 0, "loader passes");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + STAGES * TM * LDS;
     unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
     const unsigned long long tilesM = 1ull << (p.m - TM_LOG2), tilesN = 1ull << (p.n - TN_LOG2);
     const unsigned long long tiles = tilesM * tilesN;
     const unsigned long long total = tiles << ks;
-    const unsigned long long group = tilesM < 16 ? tilesM : 16;
+    const unsigned long long group = (tilesM >> p.raster_group_log2) ? (1ull << p.raster_group_log2) : tilesM;
     const unsigned long long per_group = group * tilesN;
     const unsigned long long Ksplit = (1ull << k) >> ks;
     const int KT = (int)((Ksplit + TK - 1) / TK);
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
 
     // same rasterisation as k_gemm_dmma: id -> (split, tile_m, tile_n); every count is a power of two
     const int tiles_log2 = (p.m - TM_LOG2) + (p.n - TN_LOG2);
-    const int group_log2 = (p.m - TM_LOG2) < 4 ? (p.m - TM_LOG2) : 4;
+    const int group_log2 = (p.m - TM_LOG2) < p.raster_group_log2 ? (p.m - TM_LOG2) : p.raster_group_log2;
     const int pg_log2 = group_log2 + (p.n - TN_LOG2);
     auto decode = [&](unsigned long long id, unsigned long long& split, unsigned long long& tile_m, unsigned long long& tile_n) {
         split = id >> tiles_log2;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
     constexpr int WTM = TM / WM, WTN = TN / WN;
     constexpr int MB = WTM / 8, NB = WTN / 8;
     constexpr unsigned STAGE_BYTES = (TM + TN) * TK * 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + STAGES * TM * LDS;
     unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
@@ -825,6 +825,239 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
 
 
 // ------------------------------------------------------------------------------------------------
+// Stream-K form of the warp-specialised kernel, for joins whose tile count quantises badly on the CTA slots
+// (e.g. m=11,n=10: 256 tiles of 128x64 on 296 slots — 40 SMs run one CTA while 108 run two, 0.79 of peak).
+// The K steps of ALL tiles form one sequence  g = tile * KT + kt  that is cut into gridDim.x equal ranges, one per
+// CTA (grid = the CTA slots), so every SM carries the same number of K steps.  A range is a list of segments
+// (tile, kt0, kt1): only its first segment can start inside a tile and only its last can stop short of a tile's end.
+//  * a segment that reaches its tile's end makes the CTA that tile's OWNER: it adds the partial tiles of the CTAs that
+//    computed the earlier K steps (ascending CTA order: deterministic) and scatters the result into C;
+//  * a segment that stops short ("open") is written as a partial tile, in fragment order (coalesced 16-byte stores),
+//    into the CTA's 64 KB slot of the workspace and published with a release flag.  A CTA runs its open segment FIRST,
+//    so partials exist long before their owners need them, and the only wait of the kernel is on a CTA that itself
+//    waits for nobody at that point.
+// CTA ranks are handed out by an atomic counter in start order (not blockIdx), so a waited-for CTA is always resident:
+// no co-residency assumption, safe next to other kernels.  Flags are reset by their one consumer, the counter wraps
+// to zero with the last CTA: the 4 KB flag block only has to be zero once (plan upload).
+// The segment list lives in shared memory: the main loop carries no more live state than k_gemm_dmma_ws (the
+// persistent-tile variant measured in round 1 lost 5 % to spills at the 96-register budget).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* ptr) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* ptr, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(ptr), "r"(v) : "memory");
+}
+
+
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int NPROD>
+__global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_sk(KParams p) {
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NC = WM * WN * 32;  // consumer threads
+    constexpr int TK = 16, LDS = TK, K4 = TK / 4;
+    constexpr int WTM = TM / WM, WTN = TN / WN;
+    constexpr int MB = WTM / 8, NB = WTN / 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
+    unsigned long long* cN = cM + TM;
+    unsigned long long* full = cN + TN;
+    unsigned long long* empty = full + STAGES;
+    // the segment list sits BEHIND the ring in the dynamic block: static __shared__ variables would shift the ring off its
+    // 128-byte alignment, and the swizzled rows then straddle bank lines (measured: 4x the LDGSTS shared-memory wavefronts,
+    // 2x the L2 sectors, the main loop 15-40 % slower — profiles/r02h_streamk_misaligned_ncu.md)
+    int* seg_tile = reinterpret_cast<int*>(empty + STAGES);
+    int* seg_kt0 = seg_tile + kSkMaxSegs;
+    int* seg_kt1 = seg_kt0 + kSkMaxSegs;
+    int& s_nseg = seg_kt1[kSkMaxSegs];
+    int& s_rank = seg_kt1[kSkMaxSegs + 1];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = p.k;
+    const int KT = 1 << (k - 4);
+    const int tiles_log2 = (p.m - TM_LOG2) + (p.n - TN_LOG2);
+    const int group_log2 = (p.m - TM_LOG2) < 4 ? (p.m - TM_LOG2) : 4;
+    const int pg_log2 = group_log2 + (p.n - TN_LOG2);
+    unsigned* flags = p.sk_flags;  // [0]: start-order counter, [1 + rank]: "partial of CTA rank is ready"
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 32 * NPROD);
+            mbar_init(&empty[s], WM * WN);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        // ---- this CTA's rank (start order) and its range of the global K-step sequence ----
+        const unsigned P = gridDim.x;
+        const unsigned rank = atomicInc(flags, P - 1);  // wraps to 0 after the last CTA of the launch
+        const unsigned long long G = (unsigned long long)KT << tiles_log2;
+        const unsigned long long q = G / P, r = G % P;
+        const unsigned long long g0 = rank * q + (rank < r ? rank : r), g1 = g0 + q + (rank < r ? 1 : 0);
+        const int t_first = (int)(g0 >> (k - 4)), t_last = (int)((g1 - 1) >> (k - 4));
+        const int nseg = t_last - t_first + 1;
+        const int end1 = (int)(g1 & (unsigned long long)(KT - 1));  // != 0: the last segment is open
+        const bool rotate = end1 != 0 && nseg > 1;                  // run the open segment first
+        for (int x = 0; x < nseg; x++) {
+            const int s = rotate ? (x == 0 ? nseg - 1 : x - 1) : x;
+            seg_tile[x] = t_first + s;
+            seg_kt0[x] = s == 0 ? (int)(g0 & (unsigned long long)(KT - 1)) : 0;
+            seg_kt1[x] = (s == nseg - 1 && end1 != 0) ? end1 : KT;
+        }
+        s_nseg = nseg;
+        s_rank = (int)rank;
+    }
+    for (int i = tid; i < TM; i += NC + 32 * NPROD) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NC + 32 * NPROD) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+    __syncthreads();
+    const int nseg = s_nseg;
+
+    if (warp >= WM * WN) {
+        // ===================== producer warps =====================
+        const int pw = warp - WM * WN;
+        const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
+        const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
+        const int chunk = lane & 7, r0 = lane >> 3;
+        const int dchunk = chunk ^ (r0 << 1);
+        const unsigned long long step = (4ull * NPROD) << k;
+        const unsigned long long lane_off = ((unsigned long long)(r0 + 4 * pw) << k) + chunk * 2;
+        const int dst_off = (r0 + 4 * pw) * LDS + dchunk * 2;
+        int it = 0;
+        for (int x = 0; x < nseg; x++) {
+            const unsigned tile = (unsigned)seg_tile[x];
+            const unsigned gidx = tile >> pg_log2, rr = tile & ((1u << pg_log2) - 1u);
+            const unsigned long long tile_m = ((unsigned long long)gidx << group_log2) + (rr & ((1u << group_log2) - 1u));
+            const unsigned long long tile_n = rr >> group_log2;
+            const double* a_lane = Abase + ((tile_m << TM_LOG2) << k) + lane_off;
+            const double* b_lane = Bbase + ((tile_n << TN_LOG2) << k) + lane_off;
+            const int kt1 = seg_kt1[x];
+            for (int kt = seg_kt0[x]; kt < kt1; kt++, it++) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+                const double* ag = a_lane + kt * TK;
+                const double* bg = b_lane + kt * TK;
+                double* ad = As + s * TM * LDS + dst_off;
+                double* bd = Bs + s * TN * LDS + dst_off;
+#pragma unroll
+                for (int i = 0; i < TM / 4 / NPROD; i++) cp_async16(ad + i * (4 * NPROD * LDS), ag + i * step);
+#pragma unroll
+                for (int i = 0; i < TN / 4 / NPROD; i++) cp_async16(bd + i * (4 * NPROD * LDS), bg + i * step);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&full[s]))
+                             : "memory");
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    double acc[MB][NB][2];
+    const int frag_off_a = (wm * WTM + g) * LDS;
+    const int frag_off_b = (wn * WTN + g) * LDS;
+    int koff[K4];
+#pragma unroll
+    for (int k4 = 0; k4 < K4; k4++) koff[k4] = (((2 * k4 + (t >> 1)) ^ ((g & 3) << 1)) << 1) + (t & 1);
+    double af[2][MB], bf[2][NB];
+    int it = 0;
+    for (int x = 0; x < nseg; x++) {
+#pragma unroll
+        for (int i = 0; i < MB; i++)
+#pragma unroll
+            for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int nsteps = seg_kt1[x] - seg_kt0[x];
+        for (int e = it + nsteps; it < e; it++) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            const double* as = As + s * TM * LDS + frag_off_a;
+            const double* bs = Bs + s * TN * LDS + frag_off_b;
+#pragma unroll
+            for (int i = 0; i < MB; i++) af[0][i] = as[i * 8 * LDS + koff[0]];
+#pragma unroll
+            for (int j = 0; j < NB; j++) bf[0][j] = bs[j * 8 * LDS + koff[0]];
+#pragma unroll
+            for (int k4 = 0; k4 < K4; k4++) {
+                const int cur = k4 & 1, nxt = cur ^ 1;
+                if (k4 + 1 < K4) {
+#pragma unroll
+                    for (int i = 0; i < MB; i++) af[nxt][i] = as[i * 8 * LDS + koff[(k4 + 1) % K4]];
+#pragma unroll
+                    for (int j = 0; j < NB; j++) bf[nxt][j] = bs[j * 8 * LDS + koff[(k4 + 1) % K4]];
+                }
+#pragma unroll
+                for (int i = 0; i < MB; i++)
+#pragma unroll
+                    for (int j = 0; j < NB; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- the segment is done: a partial tile for its owner, or this CTA owns the tile ----
+        const int rank = s_rank;
+        double2* slots = reinterpret_cast<double2*>(p.ws);  // slot of CTA `rank`: [MB * NB][NC] double2, fragment order
+        if (seg_kt1[x] < KT) {
+            double2* mine = slots + (size_t)rank * (MB * NB * NC) + tid;
+#pragma unroll
+            for (int i = 0; i < MB; i++)
+#pragma unroll
+                for (int j = 0; j < NB; j++) mine[(i * NB + j) * NC] = make_double2(acc[i][j][0], acc[i][j][1]);
+            __threadfence();
+            named_bar_sync(1, NC);
+            if (tid == 0) st_release_u32(flags + 1 + rank, 1u);
+            continue;
+        }
+        const unsigned tile = (unsigned)seg_tile[x];
+        if (seg_kt0[x] > 0) {
+            // contributors: the CTAs whose ranges cover K steps [tile * KT, tile * KT + kt0) — ranks first .. rank - 1
+            const unsigned P = gridDim.x;
+            const unsigned long long G = (unsigned long long)KT << tiles_log2;
+            const unsigned long long q = G / P, r = G % P;
+            const unsigned long long s0 = (unsigned long long)tile << (k - 4);
+            const int first = (int)(s0 < r * (q + 1) ? s0 / (q + 1) : r + (s0 - r * (q + 1)) / q);
+            for (int j = first; j < rank; j++) {
+                if (lane == 0)
+                    while (ld_acquire_u32(flags + 1 + j) == 0u) __nanosleep(64);
+                __syncwarp();
+                const double2* theirs = slots + (size_t)j * (MB * NB * NC) + tid;
+#pragma unroll
+                for (int i = 0; i < MB; i++)
+#pragma unroll
+                    for (int jj = 0; jj < NB; jj++) {
+                        const double2 v = __ldcg(theirs + (i * NB + jj) * NC);
+                        acc[i][jj][0] += v.x;
+                        acc[i][jj][1] += v.y;
+                    }
+                named_bar_sync(1, NC);  // every consumer warp has seen the flag and read the partial
+                if (tid == 0) flags[1 + j] = 0u;
+            }
+        }
+        const unsigned gidx = tile >> pg_log2, rr = tile & ((1u << pg_log2) - 1u);
+        const unsigned long long tile_m = ((unsigned long long)gidx << group_log2) + (rr & ((1u << group_log2) - 1u));
+        const unsigned long long tile_n = rr >> group_log2;
+        const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+        const bool vec = (p.mask_n & 1ull) != 0;
+#pragma unroll
+        for (int i = 0; i < MB; i++) {
+            const unsigned long long rbase = cbase | cM[wm * WTM + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const int col = wn * WTN + j * 8 + 2 * t;
+                if (vec) {
+                    *reinterpret_cast<double2*>(p.c + (rbase | cN[col])) = make_double2(acc[i][j][0], acc[i][j][1]);
+                } else {
+                    p.c[rbase | cN[col]] = acc[i][j][0];
+                    p.c[rbase | cN[col + 1]] = acc[i][j][1];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A TMA-fed variant of this kernel (2-D tensor maps, cp.async.bulk.tensor.2d / UTMALDG.2D from one elected thread, 128-byte
 // swizzle, one producer warp) was built and measured in round 2 and is NOT part of the build: it ran 0.4-2.3 % slower than
 // the two-producer LDGSTS feed on every join measured (profiles/r02b_kernel_lab_tma_staged.md; ncu side by side:
@@ -836,6 +1069,8 @@ template <int TM_LOG2, int TN_LOG2, int STAGES, bool SWZ = false>
 constexpr size_t gemm_ws_smem_bytes() {
     return (size_t)STAGES * ((1 << TM_LOG2) + (1 << TN_LOG2)) * (SWZ ? 16 : 20) * 8 + ((1 << TM_LOG2) + (1 << TN_LOG2)) * 8 + 2 * STAGES * 8 + 16;
 }
+
+constexpr size_t gemm_sk_smem_bytes() { return gemm_ws_smem_bytes<7, 6, 4, true>() + (3 * kSkMaxSegs + 4) * sizeof(int); }
 
 template <int TM_LOG2, int TN_LOG2, int TK, int STAGES>
 constexpr size_t gemm_smem_bytes() {
@@ -849,6 +1084,7 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76_P k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
+#define GEMM_76_SK k_gemm_dmma_sk<7, 6, 4, 2, 4, 2, 2>
 // residue-arithmetic instantiations (entry type bigint)
 #define GEMM_76_X k_gemm_dmma<7, 6, 4, 2, 16, 3, 2, true>
 #define GEMM_66_X k_gemm_dmma<6, 6, 2, 4, 16, 4, 1, true>
@@ -869,6 +1105,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WZ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_SK, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_sk_smem_bytes());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_X, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
@@ -1154,8 +1392,16 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 // short K, more tiles than CTA slots (the store-bound joins): persistent CTAs prefetch the next tiles
                 // (a shared-memory-staged epilogue writing 512-byte runs was measured in round 2 and is 25-30 % SLOWER than
                 // the direct 16-byte scatter: profiles/r02b_kernel_lab_tma_staged.md — its barriers serialise the tile)
-                GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);
-            else if (kk >= 8)
+            {
+                KParams pp = p;
+                pp.raster_group_log2 = T.store_group_log2;  // raster order of the persistent tile walk
+                GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(pp);
+            }
+            else if (op.streamk > 0 && kk >= 8) {
+                // stream-K: the K steps of all tiles in equal ranges over the CTA slots (badly quantised tile counts)
+                if (!p.sk_flags || !p.ws || op.streamk > kSkFlagBytes / 4 - 1) return cudaErrorInvalidConfiguration;
+                GEMM_76_SK<<<(unsigned)op.streamk, 320, gemm_sk_smem_bytes(), stream>>>(p);
+            } else if (kk >= 8)
                 // warp-specialised pipeline, TWO producer warps issuing LDGSTS into a swizzled 4-stage ring, mbarrier
                 // full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
                 GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);

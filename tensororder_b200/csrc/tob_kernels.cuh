@@ -20,11 +20,14 @@ struct KParams {
     const double* a;
     const double* b;
     double* c;
-    double* ws;                 // split-K partials (or nullptr)
+    double* ws;                 // split-K partials / stream-K partial tiles (or nullptr)
+    unsigned* sk_flags;         // stream-K: [0] start-order counter, [1 + rank] partial-ready flags (zero between launches)
     const long long* leaf_off;  // per-leaf slice offsets in doubles (device), may be nullptr
     int32_t a_leaf, b_leaf;     // index into leaf_off, or -1
     int32_t m, n, k;
     int32_t ksplit_log2;
+    int32_t streamk;            // > 0: stream-K launch with this many CTAs (k_gemm_dmma_sk)
+    int32_t raster_group_log2;  // persistent short-K kernel: M-tiles per raster group (set by the launcher)
     uint64_t mask_m, mask_n;
     BitRuns runs_m, runs_n;
     // exact mode (entry type "bigint"): every tensor holds residues modulo the prime `modp` < 2^23 as

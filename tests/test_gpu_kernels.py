@@ -134,6 +134,9 @@ def tuning():
         cabi.lib.tob_tuning_set(key.encode(), value)
 
 
+# stream-K forced on every eligible join (the table restricts it to 64..256 tiles)
+SK = {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40}
+
 VARIANT_CASES = [
     # long-K joins (K >= 256 per split) on the warp-specialised kernel under forced splits, swapped operands
     ({"force_ksplit_log2": 0}, (18, 16, 9)), ({"force_ksplit_log2": 2}, (19, 18, 11)), ({"force_ksplit_log2": 1}, (16, 21, 10)),
@@ -141,6 +144,12 @@ VARIANT_CASES = [
     ({"force_ksplit_log2": 1}, (18, 17, 6)), ({"persist_max_k": -1}, (16, 14, 4)),
     # deep split-K on few tiles (the mid-size class of the rank sweep)
     ({"force_ksplit_log2": 5}, (20, 20, 12)), ({"force_ksplit_log2": 7}, (22, 22, 16)), ({"force_ksplit_log2": 8}, (23, 22, 16)),
+    # stream-K (k_gemm_dmma_sk) forced on every eligible join: ranges inside one tile (many partials per owner), ranges over
+    # two tiles (config 3's dominant join), ranges over many tiles, swapped operands, a store raster order of the short-K kernel
+    (SK, (19, 17, 10)), (SK, (21, 20, 10)),
+    (SK, (19, 18, 8)), (SK, (22, 21, 9)),
+    (SK, (16, 21, 10)), (SK, (20, 20, 12)),
+    ({"store_group_log2": 0}, (16, 14, 4)), ({"store_group_log2": 2}, (17, 15, 5)),
 ]
 
 
@@ -164,7 +173,8 @@ def test_kernel_variants_match_numpy(knobs, shape, ready, tuning):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("knobs", [{"gemm_min_out": 12}, {"gemm_min_out": 12, "persist_max_k": -1}, {"max_ksplit_log2": 0}])
+@pytest.mark.parametrize("knobs", [{"gemm_min_out": 12}, {"gemm_min_out": 12, "persist_max_k": -1}, {"max_ksplit_log2": 0},
+                                   SK, {"streamk": 0}])
 @pytest.mark.parametrize("name", ["vc150_lineflow", "vc170_lineflow", "vc150_mcc_factorflow", "vc200_lineflow"])
 def test_kernel_variants_on_whole_plans(knobs, name, tuning):
     """Whole contraction trees under the variant kernels: the joins' outputs use arbitrary interleaves of the two
