@@ -169,6 +169,10 @@ int tob_plan_set_stream(tob_plan* plan, void* stream);
 /* Runs one slice op by op with CUDA events around every op; ms_per_op has n_ops entries
  * (tob_plan_num_ops).  Used for the per-node roofline report. */
 int64_t tob_plan_num_ops(const tob_plan* plan);
+/* Work of the compiled program (the SURVEY.md §8d model: 2*2^(fL+fR+k) flops per join): per slice and of the
+ * slice-invariant prologue, and the launches one slice issues.  A host that must return to its interpreter at
+ * intervals (the reference's SIGALRM TimeoutTimer, src/util/util.py:32-39) sizes its first chunk of slices from it. */
+int tob_plan_work(const tob_plan* plan, double* slice_flops, double* invariant_flops, int64_t* slice_launches);
 int tob_plan_profile(tob_plan* plan, uint64_t slice, float* ms_per_op, int64_t n_ops, double* result);
 
 /* Verification aids: run the first n_ops ops (slice-invariant list, then the per-slice list) of one slice

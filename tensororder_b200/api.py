@@ -192,7 +192,12 @@ class CompiledPlan:
         the reference's SIGALRM `TimeoutTimer` (src/util/util.py:32-39) — run between chunks of slices."""
         if count is None:
             count = (self.num_slices - first + stride - 1) // stride
-        acc, done, chunk = 0.0, 0, 1
+        # first chunk: sized from the program's work (flops at ~half the DMMA rate + ~4 us per launch), so a plan whose
+        # slices all fit the interval runs in ONE call with both slice lanes busy; later chunks from the measured time
+        sf, inv, nl = c_double(0.0), c_double(0.0), ctypes.c_int64(0)
+        cabi.lib.tob_plan_work(self._handle, byref(sf), byref(inv), byref(nl))
+        est_s = sf.value / 17e12 + nl.value * 4e-6
+        acc, done, chunk = 0.0, 0, max(1, min(count, int((target_s - inv.value / 17e12) / est_s))) if est_s > 0 else 1
         total_ms, launches = 0.0, 0
         gemm = [0.0, 0.0, 0]
         while done < count or (count == 0 and done == 0):

@@ -66,6 +66,7 @@ SYMBOLS = {
     "tob_plan_last_gemm": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     "tob_plan_set_stream": (c_int32, [c_void_p, c_void_p]),
     "tob_plan_num_ops": (c_int64, [c_void_p]),
+    "tob_plan_work": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
     "tob_plan_profile": (c_int32, [c_void_p, c_uint64, POINTER(c_float), c_int64, POINTER(c_double)]),
     "tob_plan_debug_run": (c_int32, [c_void_p, c_uint64, c_int64]),
     "tob_plan_debug_read": (c_int32, [c_void_p, c_int32, c_int64, c_int64, POINTER(c_double)]),

@@ -63,7 +63,7 @@ Tuning& tuning() {
         x.streamk = TOB_TUNE_STREAMK;
         x.streamk_min_tiles_log2 = TOB_TUNE_STREAMK_MIN_TILES_LOG2;
         x.streamk_max_tiles_log2 = TOB_TUNE_STREAMK_MAX_TILES_LOG2;
-        x.store_bulk = TOB_TUNE_STORE_BULK;
+        x.store_tile = TOB_TUNE_STORE_TILE;
         x.streamk_fix_us = TOB_TUNE_STREAMK_FIX_US;
         x.store_group_log2 = TOB_TUNE_STORE_GROUP_LOG2;
         return x;
@@ -86,7 +86,7 @@ const TuneField kTuneFields[] = {
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
     {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
-    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"store_bulk", &Tuning::store_bulk, nullptr},
+    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"store_tile", &Tuning::store_tile, nullptr},
     {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };
 // "gemm_min_out" sets every k at once, "gemm_min_out.<k>" one entry

@@ -383,6 +383,16 @@ int64_t tob_plan_describe(const tob_plan* p, char* buf, int64_t cap) {
 }
 
 int64_t tob_plan_num_ops(const tob_plan* p) { return (int64_t)(p->prog.invariant_ops.size() + p->prog.slice_ops.size()); }
+int tob_plan_work(const tob_plan* p, double* slice_flops, double* invariant_flops, int64_t* slice_launches) {
+    if (!p) { set_error("null plan"); return TOB_E_INVALID; }
+    double sf = 0, inv = 0;
+    for (const Op& op : p->prog.slice_ops) sf += op.flops;
+    for (const Op& op : p->prog.invariant_ops) inv += op.flops;
+    if (slice_flops) *slice_flops = sf;
+    if (invariant_flops) *invariant_flops = inv;
+    if (slice_launches) *slice_launches = (int64_t)p->prog.slice_ops.size() + 1;
+    return TOB_OK;
+}
 
 static void release_lanes(tob_plan* p) {
     for (int l = 0; l < kMaxLanes; l++) {

@@ -137,7 +137,7 @@ struct Tuning {
     int streamk_max_tiles_log2;  // ... and at most this many (ranges over several tiles lose the L2 locality of the raster)
     double streamk_fix_us;  // modelled cost of the partial-tile exchange
     int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
-    int store_bulk;         // persistent short-K kernel: 1 = tiles leave through shared memory as bulk (TMA) stores
+    int store_tile;         // persistent short-K kernel at K = 16: 1 = rows stored while the next rows compute (k_gemm_dmma_p1), 0 = whole tile first
 };
 Tuning& tuning();
 bool tuning_set(const char* key, double value);

@@ -621,6 +621,139 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K <= 16 (ONE K step per tile — every join the persistent kernel is dispatched for): the same persistent tile walk,
+// but a warp finishes its 32x32 block RP rows of 8 at a time and stores each group of rows while the DMMAs of the
+// next group issue.  In k_gemm_dmma_p a tile is 64 DMMAs per warp followed by a burst of 16 stores per thread, the
+// CTAs of an SM drift into the same phase, and the DMMA pipe (55 % busy at k = 4, ncu) and the store path take turns
+// instead of overlapping; here both are fed all the time.  The B fragments of the whole K step stay in registers
+// (NB x 4 doubles), the accumulators shrink from 64 to 16 * RP registers.
+// ------------------------------------------------------------------------------------------------
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int RP>
+__global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) {
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NT = WM * WN * 32;
+    constexpr int WTM = TM / WM, WTN = TN / WN;
+    constexpr int MB = WTM / 8, NB = WTN / 8;
+    constexpr int TK = 16, LDS = TK + 4, CHUNKS = TK / 2, RPP = NT / CHUNKS, K4 = TK / 4;
+    static_assert(TM % RPP == 0 && TN % RPP == 0 && MB % RP == 0, "loader passes / row groups");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
+    unsigned long long* cN = cM + TM;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    const int k = p.k, ks = p.ksplit_log2;
+
+    for (int i = tid; i < TM; i += NT) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NT) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+
+    const int tiles_log2 = (p.m - TM_LOG2) + (p.n - TN_LOG2);
+    const unsigned long long tiles = 1ull << tiles_log2;
+    const unsigned long long total = tiles << ks;
+    const int group_log2 = (p.m - TM_LOG2) < p.raster_group_log2 ? (p.m - TM_LOG2) : p.raster_group_log2;
+    const int pg_log2 = group_log2 + (p.n - TN_LOG2);
+    const unsigned long long Ksplit = (1ull << k) >> ks;   // <= TK
+    const int k4_end = (int)((Ksplit + 3) / 4);
+    const long long nmine = total > blockIdx.x ? (long long)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
+    const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
+    auto decode = [&](unsigned long long id, unsigned long long& split, unsigned long long& tile_m, unsigned long long& tile_n) {
+        split = id >> tiles_log2;
+        const unsigned long long tid_in = id & (tiles - 1);
+        const unsigned long long gidx = tid_in >> pg_log2, r = tid_in & ((1ull << pg_log2) - 1ull);
+        tile_m = (gidx << group_log2) + (r & ((1ull << group_log2) - 1ull));
+        tile_n = r >> group_log2;
+    };
+
+    // ---- loader: one stage = the operands of one tile; runs STAGES-1 tiles ahead ----
+    const int chunk = tid % CHUNKS, row0 = tid / CHUNKS;
+    const unsigned long long pass_stride = (unsigned long long)RPP << k;
+    const int dst_off = row0 * LDS + chunk * 2;
+    const int nbytes = ((unsigned long long)(chunk * 2) < Ksplit) ? 16 : 0;  // K = 2, 4, 8: zero-fill the tail chunks
+    const int back = nbytes ? 0 : chunk * 2;                                 // keep the (unused) source address inside the row
+    auto load_tile = [&](int s, unsigned long long id) {
+        unsigned long long split, tile_m, tile_n;
+        decode(id, split, tile_m, tile_n);
+        const double* ag = Abase + ((tile_m << TM_LOG2) << k) + split * Ksplit + ((unsigned long long)row0 << k) + chunk * 2 - back;
+        const double* bg = Bbase + ((tile_n << TN_LOG2) << k) + split * Ksplit + ((unsigned long long)row0 << k) + chunk * 2 - back;
+        double* as = As + s * TM * LDS + dst_off;
+        double* bs = Bs + s * TN * LDS + dst_off;
+#pragma unroll
+        for (int i = 0; i < TM / RPP; i++) cp_async16_zfill(as + i * RPP * LDS, ag + i * pass_stride, nbytes);
+#pragma unroll
+        for (int i = 0; i < TN / RPP; i++) cp_async16_zfill(bs + i * RPP * LDS, bg + i * pass_stride, nbytes);
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nmine) load_tile(s, blockIdx.x + (unsigned long long)s * gridDim.x);
+        cp_async_commit();
+    }
+    const int frag_off_a = (wm * WTM + g) * LDS + t;
+    const int frag_off_b = (wn * WTN + g) * LDS + t;
+    const bool vec = (p.mask_n & 1ull) != 0;
+    auto store_rows = [&](const double (&v)[RP][NB][2], double* out, const unsigned long long (&rb)[RP]) {
+#pragma unroll
+        for (int r = 0; r < RP; r++)
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                const int col = wn * WTN + j * 8 + 2 * t;
+                if (vec) {
+                    *reinterpret_cast<double2*>(out + (rb[r] | cN[col])) = make_double2(v[r][j][0], v[r][j][1]);
+                } else {
+                    out[rb[r] | cN[col]] = v[r][j][0];
+                    out[rb[r] | cN[col + 1]] = v[r][j][1];
+                }
+            }
+    };
+    for (long long s = 0; s < nmine; s++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const long long nk = s + STAGES - 1;
+        if (nk < nmine) load_tile((int)(nk % STAGES), blockIdx.x + (unsigned long long)nk * gridDim.x);
+        cp_async_commit();
+        const double* as = As + (int)(s % STAGES) * TM * LDS + frag_off_a;
+        const double* bs = Bs + (int)(s % STAGES) * TN * LDS + frag_off_b;
+        unsigned long long split, tile_m, tile_n;
+        decode(blockIdx.x + (unsigned long long)s * gridDim.x, split, tile_m, tile_n);
+        double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
+        const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+        double bf[NB][K4];
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+#pragma unroll
+            for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = (k4 < k4_end) ? bs[j * 8 * LDS + k4 * 4] : 0.0;
+#pragma unroll
+        for (int i0 = 0; i0 < MB; i0 += RP) {
+            double acc[RP][NB][2];
+            double af[RP][K4];
+#pragma unroll
+            for (int r = 0; r < RP; r++) {
+#pragma unroll
+                for (int k4 = 0; k4 < K4; k4++) af[r][k4] = (k4 < k4_end) ? as[(i0 + r) * 8 * LDS + k4 * 4] : 0.0;
+#pragma unroll
+                for (int j = 0; j < NB; j++) acc[r][j][0] = acc[r][j][1] = 0.0;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < K4; k4++) {
+                if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
+#pragma unroll
+                for (int r = 0; r < RP; r++)
+#pragma unroll
+                    for (int j = 0; j < NB; j++) dmma884(acc[r][j][0], acc[r][j][1], af[r][k4], bf[j][k4]);
+            }
+            unsigned long long rb[RP];
+#pragma unroll
+            for (int r = 0; r < RP; r++) rb[r] = cbase | cM[wm * WTM + (i0 + r) * 8 + g];
+            store_rows(acc, Cout, rb);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Warp-specialised DMMA GEMM: one producer warp streams whole 128-byte operand rows into the padded
 // K-major tiles with bulk async copies (cp.async.bulk, SASS UBLKCP) that signal a per-stage "full"
 // mbarrier by transaction bytes; eight consumer warps wait on "full", run the DMMA steps, and arrive on
@@ -1082,6 +1215,11 @@ constexpr size_t gemm_smem_bytes() {
 #define GEMM_76 k_gemm_dmma<7, 6, 4, 2, 16, 3, 2>
 #define GEMM_66 k_gemm_dmma<6, 6, 2, 4, 16, 4, 1>
 #define GEMM_76_P k_gemm_dmma_p<7, 6, 4, 2, 16, 3, 2>
+// K = 16: one K step per tile, two row groups of 8 stored while the next two compute.  Measured next to it and not kept
+// (profiles/r02h_kernel_lab_store_*.md): one row group at a time (0.83 of HBM at k = 4: too few independent DMMA chains),
+// three CTAs per SM at 80 registers (0.80), stores deferred behind the next group's DMMAs (0.83), 64x64 tiles at four
+// CTAs per SM on k_gemm_dmma_p (0.83, and 0.73 instead of 0.72 of the FP64 peak at k = 5).
+#define GEMM_76_P1 k_gemm_dmma_p1<7, 6, 4, 2, 3, 2, 2>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 #define GEMM_76_SK k_gemm_dmma_sk<7, 6, 4, 2, 4, 2, 2>
@@ -1101,6 +1239,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_66, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<6, 6, 16, 4>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_P1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
@@ -1395,7 +1535,11 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             {
                 KParams pp = p;
                 pp.raster_group_log2 = T.store_group_log2;  // raster order of the persistent tile walk
-                GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(pp);
+                if (T.store_tile == 1 && kk == 4)
+                    // K = 16 (the DMMA time is 3/4 of the store time): rows leave while the next rows compute, 0.78 -> 0.89 of HBM
+                    GEMM_76_P1<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(pp);
+                else
+                    GEMM_76_P<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(pp);
             }
             else if (op.streamk > 0 && kk >= 8) {
                 // stream-K: the K steps of all tiles in equal ranges over the CTA slots (badly quantised tile counts)

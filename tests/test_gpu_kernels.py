@@ -150,6 +150,8 @@ VARIANT_CASES = [
     (SK, (19, 18, 8)), (SK, (22, 21, 9)),
     (SK, (16, 21, 10)), (SK, (20, 20, 12)),
     ({"store_group_log2": 0}, (16, 14, 4)), ({"store_group_log2": 2}, (17, 15, 5)),
+    # K = 16: the row-streamed persistent kernel (table default) under a forced split, and the whole-tile kernel it replaced
+    ({"force_ksplit_log2": 1}, (20, 19, 5)), ({"store_tile": 0}, (16, 14, 4)), ({"store_tile": 1}, (14, 17, 4)),
 ]
 
 
@@ -174,7 +176,7 @@ def test_kernel_variants_match_numpy(knobs, shape, ready, tuning):
 
 
 @pytest.mark.parametrize("knobs", [{"gemm_min_out": 12}, {"gemm_min_out": 12, "persist_max_k": -1}, {"max_ksplit_log2": 0},
-                                   SK, {"streamk": 0}])
+                                   SK, {"streamk": 0, "store_tile": 0}])
 @pytest.mark.parametrize("name", ["vc150_lineflow", "vc170_lineflow", "vc150_mcc_factorflow", "vc200_lineflow"])
 def test_kernel_variants_on_whole_plans(knobs, name, tuning):
     """Whole contraction trees under the variant kernels: the joins' outputs use arbitrary interleaves of the two

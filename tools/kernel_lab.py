@@ -21,7 +21,7 @@ def tset(**kv):
 
 
 DEFAULTS = {}
-for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "store_group_log2", "store_bulk", "force_ksplit_log2", "persist_max_k"):
+for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "store_group_log2", "store_tile", "force_ksplit_log2", "persist_max_k"):
     v = ctypes.c_double()
     assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0
     DEFAULTS[key] = v.value
@@ -104,14 +104,15 @@ if what in ("streamk", "all"):
         s2, b2, out = time_join(m, n, k, {}, reps)
         rows.append(report(m, n, k, "table default", s2, b2))
 if what in ("store", "all"):
-    for (m, n, k) in [(14, 14, 4), (15, 15, 4), (14, 14, 2), (15, 15, 2), (16, 16, 2), (15, 14, 5), (15, 14, 3), (14, 13, 1)]:
+    for (m, n, k) in [(14, 14, 4), (15, 15, 4), (14, 14, 2), (16, 16, 2), (15, 14, 3), (14, 13, 1), (13, 11, 4), (15, 14, 5)]:
         ref = None
-        for g in (4, 2, 1, 0):
-            s, b, out = time_join(m, n, k, {"store_group_log2": g}, 3)
+        variants = [("whole tile, then stores (k_gemm_dmma_p)", {"store_tile": 0}), ("table default", {})]
+        for label, knobs in variants:
+            s, b, out = time_join(m, n, k, knobs, 3)
             if ref is None:
                 ref = out
-            assert torch.equal(out, ref)
-            rows.append(report(m, n, k, "persistent, raster group 2^%d" % g, s, b))
+            assert torch.equal(out, ref), (m, n, k, label)
+            rows.append(report(m, n, k, label, s, b))
         del ref, out
         torch.cuda.empty_cache()
     # write-only and copy ceilings for the store-bound joins
