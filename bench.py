@@ -605,6 +605,41 @@ def b200_arm(args, rank, world, local_rank):
         gemm_flops += g[1]
         gemm_launches += g[2]
         seq_ms += it["cp"].last_ms
+    # ---- where this rank's device time goes: the replicated slice-invariant prologues of the shared instances, its
+    # slices, the unsliced instances it owns (per-op CUDA events, tob_plan_profile: sequential, every small op carries
+    # its event pair) and the count all-reduce ----
+    split = [0.0, 0.0, 0.0, 0.0]
+    for it in mine:
+        cp = it["cp"]
+        cp.set_gemm_timing(False)
+        ms, _ = cp.profile(rank if it["owner"] is None else 0)
+        n_inv = len(cp.describe()["invariant_ops"])
+        pro, per_slice = float(sum(ms[:n_inv])), float(sum(ms[n_inv:]))
+        if it["owner"] is None:
+            split[0] += pro
+            split[1] += per_slice * ((it["nsl"] - rank + world - 1) // world)
+        else:
+            split[2] += pro + per_slice * it["nsl"]
+    if world > 1:
+        probe = torch.zeros(4, dtype=torch.float64, device=dev)
+        for rep in range(12):
+            if rep == 2:
+                torch.cuda.synchronize(dev)
+                a0 = torch.cuda.Event(enable_timing=True)
+                a1 = torch.cuda.Event(enable_timing=True)
+                a0.record()
+            dist.all_reduce(probe)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        split[3] = a0.elapsed_time(a1) / 10.0
+    split_t = torch.tensor(split, dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(split_t) for _ in range(world)]
+        dist.all_gather(gathered, split_t)
+    else:
+        gathered = [split_t]
+    rank_split = [{"rank": r, "shared_prologues_ms": float(g_[0]), "own_slices_ms": float(g_[1]), "unsliced_ms": float(g_[2]),
+                   "count_allreduce_ms": float(g_[3])} for r, g_ in enumerate(gathered)]
     for it in mine:
         it["cp"].close()
         del it["cp"]
@@ -713,6 +748,10 @@ def b200_arm(args, rank, world, local_rank):
             "issue": "sequential" if args.sequential else "async: all of a rank's instances in flight",
             "rank0": {"instances": [it["n"] for it in mine], "sequential_device_ms": seq_ms,
                       "modelled_load_s": load},
+            "rank_split": {"note": "per rank, sequential per-op event times (tob_plan_profile): slice-invariant prologues of the "
+                                   "instances every rank shares (replicated), this rank's slices of them, the unsliced instances "
+                                   "it owns, one 32-byte count all-reduce (the only collective of a contraction)",
+                           "ranks": rank_split},
         }
         if gemm_launches > 0:
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12

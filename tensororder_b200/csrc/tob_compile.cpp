@@ -64,6 +64,8 @@ Tuning& tuning() {
         x.streamk_min_tiles_log2 = TOB_TUNE_STREAMK_MIN_TILES_LOG2;
         x.streamk_max_tiles_log2 = TOB_TUNE_STREAMK_MAX_TILES_LOG2;
         x.store_tile = TOB_TUNE_STORE_TILE;
+        x.permute_low_bits = 0;
+        x.permute_ctas_per_sm = 0;
         x.streamk_fix_us = TOB_TUNE_STREAMK_FIX_US;
         x.store_group_log2 = TOB_TUNE_STORE_GROUP_LOG2;
         return x;
@@ -87,6 +89,7 @@ const TuneField kTuneFields[] = {
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
     {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
     {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"store_tile", &Tuning::store_tile, nullptr},
+    {"permute_low_bits", &Tuning::permute_low_bits, nullptr}, {"permute_ctas_per_sm", &Tuning::permute_ctas_per_sm, nullptr},
     {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };
 // "gemm_min_out" sets every k at once, "gemm_min_out.<k>" one entry

@@ -137,6 +137,7 @@ struct Tuning {
     int streamk_max_tiles_log2;  // ... and at most this many (ranges over several tiles lose the L2 locality of the raster)
     double streamk_fix_us;  // modelled cost of the partial-tile exchange
     int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
+    int permute_low_bits, permute_ctas_per_sm;  // stand-alone permutation kernel: tile shape / grid (0 = defaults)
     int store_tile;         // persistent short-K kernel at K = 16: 1 = rows stored while the next rows compute (k_gemm_dmma_p1), 0 = whole tile first
 };
 Tuning& tuning();

@@ -1664,8 +1664,8 @@ cudaError_t launch_permute(const double* in, double* out, int rank, const int32_
         return cudaGetLastError();
     }
     // tile = low TB output bits  U  output bits fed by the low TB input bits, padded to >= 8 bits
-    static const int tb_env = getenv("TOB_PERMUTE_TB") ? atoi(getenv("TOB_PERMUTE_TB")) : 0;
-    const int TB = tb_env > 0 ? (rank >= 2 * tb_env ? tb_env : 4) : (rank >= 12 ? 6 : 4);
+    const int tb_knob = tuning().permute_low_bits;  // 0: 6 low bits of both sides from rank 12 on, else 4
+    const int TB = tb_knob > 0 ? (rank >= 2 * tb_knob ? tb_knob : 4) : (rank >= 12 ? 6 : 4);
     bool in_tile[64] = {false};
     int tbits = 0;
     for (int q = 0; q < rank; q++)
@@ -1710,7 +1710,7 @@ cudaError_t launch_permute(const double* in, double* out, int rank, const int32_
     for (int q = 0; q < rank; q++)
         if (!in_tile[q]) { p.rest_out[p.nrest] = (uint8_t)q; p.rest_in[p.nrest] = (uint8_t)src_bit[q]; p.nrest++; }
     const unsigned long long ntiles = 1ull << p.nrest;
-    static const int bl_env = getenv("TOB_PERMUTE_BLOCKS") ? atoi(getenv("TOB_PERMUTE_BLOCKS")) : 8;
+    const int bl_env = tuning().permute_ctas_per_sm > 0 ? tuning().permute_ctas_per_sm : 8;
     const unsigned blocks = (unsigned)(ntiles < (unsigned long long)num_sms() * bl_env ? ntiles : (unsigned long long)num_sms() * bl_env);
     const size_t smem = ((size_t)1 << n) * 8;
     if (rank <= 32) {

@@ -111,6 +111,87 @@ def test_forced_generic_policy_and_gemm_selection():
     assert all(op["kind"] in (0, 2, 3) for op in forced["slice_ops"])
 
 
+def _streamk_partition(tiles_log2, k, ctas):
+    """The range/segment arithmetic of k_gemm_dmma_sk (csrc/tob_kernels.cu), restated: returns for every CTA rank its
+    segments in PROCESSING order, and for every tile whose finishing CTA did not start it the (owner, first contributor)."""
+    kt = 1 << (k - 4)
+    total = kt << tiles_log2
+    q, r = divmod(total, ctas)
+    segs, owners = {}, {}
+    for rank in range(ctas):
+        g0 = rank * q + min(rank, r)
+        g1 = g0 + q + (1 if rank < r else 0)
+        t_first, t_last = g0 >> (k - 4), (g1 - 1) >> (k - 4)
+        nseg, end1 = t_last - t_first + 1, g1 & (kt - 1)
+        rotate = end1 != 0 and nseg > 1
+        mine = []
+        for x in range(nseg):
+            s_ = (nseg - 1 if x == 0 else x - 1) if rotate else x
+            kt0 = (g0 & (kt - 1)) if s_ == 0 else 0
+            kt1 = end1 if (s_ == nseg - 1 and end1 != 0) else kt
+            mine.append((t_first + s_, kt0, kt1))
+            if kt1 == kt and kt0 > 0:
+                s0 = (t_first + s_) << (k - 4)
+                owners[t_first + s_] = (rank, s0 // (q + 1) if s0 < r * (q + 1) else r + (s0 - r * (q + 1)) // q)
+        segs[rank] = mine
+    return kt, segs, owners
+
+
+@pytest.mark.parametrize("tiles_log2,k", [(8, 10), (8, 9), (6, 12), (3, 10), (12, 9), (7, 8), (10, 8), (0, 13)])
+def test_streamk_partition_covers_every_k_step_once(tiles_log2, k):
+    """Stream-K: every (tile, K step) belongs to exactly one CTA; a CTA publishes at most one partial tile and does so in its
+    FIRST segment (so the owner's wait never chains); an owner's contributors are exactly the lower ranks holding the
+    tile's earlier K steps, in order — the deterministic summation order of the kernel."""
+    ctas = 296
+    kt, segs, owners = _streamk_partition(tiles_log2, k, ctas)
+    if (kt << tiles_log2) < ctas:
+        pytest.skip("fewer K steps than CTAs: choose_kernel never picks stream-K here")
+    seen, partial = set(), {}
+    for rank, mine in segs.items():
+        for pos, (tile, kt0, kt1) in enumerate(mine):
+            for step in range(kt0, kt1):
+                assert (tile, step) not in seen
+                seen.add((tile, step))
+            if kt1 < kt:
+                assert rank not in partial and pos == 0
+                partial[rank] = (tile, kt0, kt1)
+    assert len(seen) == kt << tiles_log2
+    used = set()
+    for tile, (owner, first) in owners.items():
+        steps = []
+        for j in range(first, owner):
+            t, a, b = partial[j]
+            assert t == tile and j < owner
+            steps += list(range(a, b))
+            used.add(j)
+        own_start = [kt0 for (t, kt0, kt1) in segs[owner] if t == tile][0]
+        assert steps == list(range(own_start))
+    assert used == set(partial)
+
+
+def test_streamk_is_chosen_for_badly_quantised_tile_counts_only():
+    """Config 3's dominant joins (m=11, n=10, k=10: 256 tiles of 128x64 on 296 CTA slots) run on the stream-K kernel with one
+    64 KB partial-tile slot per CTA in the workspace; the 2048-tile joins of the sliced family members do not."""
+    import ctypes
+
+    from tensororder_b200 import cabi
+
+    flat = flatten_plan(load_golden("vc150_mcc_factorflow").as_execution_plan())
+    desc = CompiledPlan(flat).describe()
+    sk = [op for op in desc["slice_ops"] + desc["invariant_ops"] if op["kind"] == 1 and op["streamk"] > 0]
+    assert sk and all(op["ksplit_log2"] == 0 and 6 <= (op["m"] - 7) + (op["n"] - 6) <= 8 and op["k"] >= 8 for op in sk)
+    assert (11, 10, 10) in {(op["m"], op["n"], op["k"]) for op in sk}
+    assert desc["ws_doubles"] >= max(op["streamk"] for op in sk) * 128 * 64
+    big = CompiledPlan(flatten_plan(load_golden("vc210_lineflow").variant("min3").as_execution_plan())).describe()
+    assert all(op["streamk"] == 0 for op in big["slice_ops"] if op["kind"] == 1 and op["m"] + op["n"] >= 24)
+    assert cabi.lib.tob_tuning_set(b"streamk", 0.0) == 0
+    try:
+        off = CompiledPlan(flat).describe()
+        assert all(op.get("streamk", 0) == 0 for op in off["slice_ops"] + off["invariant_ops"] if op["kind"] in (0, 1))
+    finally:
+        cabi.lib.tob_tuning_set(b"streamk", 1.0)
+
+
 @pytest.mark.parametrize("name,variant", [("vc50_lineflow", None), ("vc100_lineflow", "min4"), ("vc150_lineflow", None)])
 def test_micro_subtrees(name, variant):
     """Mini joins collapse into one launch per stage (level of a phase); results are unchanged with the
