@@ -198,7 +198,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
             if (T.streamk > 0 && op->tm_log2 == 7 && op->tn_log2 == 6) {
                 int ctas = 0;
                 const double t = streamk_time_model_us(m, n, k, &ctas);
-                if (t > 0.0 && (T.streamk >= 2 || (T.force_ksplit_log2 < 0 && t < best * 0.97))) {
+                if (t > 0.0 && (T.streamk >= 2 || (T.force_ksplit_log2 < 0 && t < best * 0.98))) {
                     op->streamk = ctas;
                     ks = 0;
                 }

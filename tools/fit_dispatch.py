@@ -6,7 +6,9 @@ under `tob_tuning_set` overrides and derives
      split of a grid of GEMM shapes is timed, the constants are fitted to the measured times (least squares on
      log(model / measured)), and the table prints the split the fitted model picks next to the measured best;
   B. the generic <-> DMMA GEMM crossover as a table by k (gemm_min_out[k]: the smallest m + n from which the GEMM wins);
-  C. the generic kernel classes (t1_max_k, t1_small_*, t32_max_k) and the persistent short-K range (persist_max_k).
+  C. the generic kernel classes (t1_max_k, t1_small_*, t32_max_k) and the persistent short-K range (persist_max_k);
+  D. the stream-K range (streamk_min/max_tiles_log2: tile counts where k_gemm_dmma_sk beats the best split of the
+     one-tile-per-CTA kernel) and its fixed cost (streamk_fix_us), and the K = 16 store kernel (store_tile).
 
 Usage (GPU box):  python tools/fit_dispatch.py [--quick]
 Writes gpurun_out/dispatch_fit.json (raw measurements) and gpurun_out/tob_dispatch_table.h (copy it over
@@ -44,7 +46,8 @@ def tget(key):
 
 KEYS = ["gemm_min_free", "gemm_min_k", "gemm_smallk_min_free", "t1_max_k", "t1_small_out", "t1_small_max_k",
         "t32_max_k", "t32_min_out", "persist_max_k", "sm_gflops", "alone_frac", "gemm_fix_us", "reduce_gbs",
-        "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2"] + ["gemm_min_out.%d" % i for i in range(17)]
+        "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2", "streamk", "streamk_min_tiles_log2",
+        "streamk_max_tiles_log2", "streamk_fix_us", "store_tile"] + ["gemm_min_out.%d" % i for i in range(17)]
 for k_ in KEYS:
     DEFAULTS[k_] = tget(k_)
 
@@ -71,7 +74,7 @@ def time_join(m, n, k, policy=0, reps=5, ws_log2=None):
     """Best-of-reps contraction time (us) and the kernel kind of C[2^(m+n)] = A[2^(m+k)] . B[2^(n+k)]."""
     ra, rb, rc = m + k, n + k, m + n
     a, b, c = buf(1 << ra, "a"), buf(1 << rb, "b"), buf(1 << rc, "c")
-    ws_n = 1 << (ws_log2 if ws_log2 is not None else min(rc + 8, 28))
+    ws_n = max(1 << (ws_log2 if ws_log2 is not None else min(rc + 8, 28)), 300 * 8192)  # >= one stream-K slot per CTA
     ws = buf(ws_n + 512, "ws")
     aa = np.arange(ra - k, ra, dtype=np.int32)
     ab = np.arange(rb - k, rb, dtype=np.int32)
@@ -236,6 +239,45 @@ out["persistent"] = persist
 persist_max_k = max([r["k"] for r in persist if r["persistent_us"] <= r["one_tile_per_cta_us"] * 1.01] or [int(DEFAULTS["persist_max_k"])])
 
 # ---------------------------------------------------------------------------------------------------
+# D. stream-K range and fixed cost; the K = 16 store kernel
+# ---------------------------------------------------------------------------------------------------
+sk_rows = []
+for tl in range(4, 11):  # 16 .. 1024 tiles of 128x64
+    m, n = 7 + (tl + 1) // 2, 6 + tl // 2
+    for k in (10, 12):
+        if m + n + k > 34:
+            continue
+        tset("streamk", 0)
+        dp_us, _ = time_join(m, n, k)
+        tset("streamk", 2); tset("streamk_min_tiles_log2", 0); tset("streamk_max_tiles_log2", 40)
+        sk_us, _ = time_join(m, n, k)
+        restore()
+        steps = math.ceil((1 << (tl + k - 4)) / 296.0)
+        fix = sk_us - steps * (2.0 * 2 ** 17 / (DEFAULTS["sm_gflops"] * 1e3 / 2.0)) - DEFAULTS["gemm_fix_us"]
+        sk_rows.append({"m": m, "n": n, "k": k, "tiles_log2": tl, "best_split_us": dp_us, "streamk_us": sk_us, "residual_fix_us": fix})
+        print("  stream-K m=%d n=%d k=%d (%d tiles): best split %.1f us, stream-K %.1f us" % (m, n, k, 1 << tl, dp_us, sk_us))
+out["streamk"] = sk_rows
+# the range: from the first to the last tile count where stream-K wins by >= 3 % at some K, as long as it is no worse than
+# 1 % everywhere in between (inside the range the time model decides per join); the fixed cost: the smallest residual
+# measured time - K steps * step time - launch cost over the winning joins (optimistic, the 3 % margin covers the rest)
+wins = sorted({r["tiles_log2"] for r in sk_rows if r["streamk_us"] < 0.97 * r["best_split_us"]})
+tie_or_win = {r["tiles_log2"] for r in sk_rows if r["streamk_us"] <= 1.01 * r["best_split_us"]}
+sk_min = wins[0] if wins else 99
+sk_max = wins[-1] if wins else 99
+while wins and not all(t in tie_or_win for t in range(sk_min, sk_max + 1)):
+    sk_max -= 1
+win_fix = [r["residual_fix_us"] for r in sk_rows if sk_min <= r["tiles_log2"] <= sk_max and r["streamk_us"] < 0.97 * r["best_split_us"]]
+sk_fix = int(math.ceil(min(win_fix))) if win_fix else int(DEFAULTS["streamk_fix_us"])
+store = {}
+for v in (0, 1):
+    tset("store_tile", v)
+    store[v] = [time_join(m, n, 4)[0] for (m, n) in ((14, 14), (15, 14), (13, 12))]
+    restore()
+out["store_tile"] = store
+store_tile = 1 if sum(store[1]) < sum(store[0]) else 0
+print("  K = 16 store kernel: whole tile %s us, row-streamed %s us" % (["%.1f" % x for x in store[0]], ["%.1f" % x for x in store[1]]))
+
+# ---------------------------------------------------------------------------------------------------
 table = {
     "GEMM_MIN_FREE": int(DEFAULTS["gemm_min_free"]), "GEMM_MIN_K": int(DEFAULTS["gemm_min_k"]),
     "GEMM_SMALLK_MIN_FREE": int(DEFAULTS["gemm_smallk_min_free"]),
@@ -245,6 +287,9 @@ table = {
     "PERSIST_MAX_K": persist_max_k, "SM_GFLOPS": DEFAULTS["sm_gflops"], "ALONE_FRAC": fit["alone_frac"],
     "GEMM_FIX_US": float(fit["gemm_fix_us"]), "REDUCE_GBS": float(fit["reduce_gbs"]), "REDUCE_FIX_US": float(fit["reduce_fix_us"]),
     "MAX_KSPLIT_LOG2": int(DEFAULTS["max_ksplit_log2"]), "MIN_K_PER_SPLIT_LOG2": int(DEFAULTS["min_k_per_split_log2"]),
+    "STREAMK": 1 if wins else 0, "STREAMK_MIN_TILES_LOG2": sk_min if wins else int(DEFAULTS["streamk_min_tiles_log2"]),
+    "STREAMK_MAX_TILES_LOG2": sk_max if wins else int(DEFAULTS["streamk_max_tiles_log2"]), "STREAMK_FIX_US": sk_fix,
+    "STORE_TILE": store_tile,
 }
 out["table"] = table
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
@@ -253,7 +298,7 @@ src = open(os.path.join(REPO, "tensororder_b200", "csrc", "tob_dispatch_table.h"
 lines = []
 for ln in src:
     if ln.startswith("// generated:"):
-        ln = "// generated: %s on %s by tools/fit_dispatch.py (fit rms log error %.3f over %d timings; raw: profiles/r02e_dispatch_fit.json)" % (
+        ln = "// generated: %s on %s by tools/fit_dispatch.py (fit rms log error %.3f over %d timings; raw: profiles/r02i_dispatch_fit.json)" % (
             out["when"], out["gpu"], out["fit"]["rms_log_error"], len(rows))
     if ln.startswith("#define TOB_TUNE_"):
         name = ln.split()[1][len("TOB_TUNE_"):]
