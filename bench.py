@@ -51,7 +51,7 @@ METRIC = "contraction s/instance (plan excluded)"
 UNIT = "s/instance"
 FP64_CUBLAS_CALIBRATION = 35.49  # cuBLAS DGEMM 8192^3 on this pool's B200s, round 1 (profiles/r01_fp64_calibration.txt)
 FP64_DMMA_PIPE = 37.1            # raw DMMA.8x8x4 issue peak measured by tools/fp64_peak.cu (same file)
-E2E_THREADS = 4                   # host threads of the e2e arm at N = 1: the three sliced instances and the small ones
+E2E_THREADS = int(os.environ.get("TOB_BENCH_E2E_THREADS", "8"))  # host threads of the e2e arm at N = 1 (sliced instances one each, the small ones share the rest)
 
 
 def measured_peaks():
@@ -693,6 +693,9 @@ def b200_arm(args, rank, world, local_rank):
         results = [(it, contract_one(it)) for it in groups[0]]
         for g, fut in zip(groups[1:], side):
             results += list(zip(g, fut.result()))
+        timeline = [{"n": it["n"], "thread": next(gi for gi, g in enumerate(groups) if it in g),
+                     "ms_from_step_start": [round((x - t0) * 1e3, 2) for x in stats["t_call"]]}
+                    for it, (got, stats) in results if it["model_s"] >= 1e-3]
         for it, (got, stats) in results:
             host[index[it["name"]]] = got
             h2d += stats["h2d_bytes"]
@@ -743,6 +746,9 @@ def b200_arm(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
                     "step_seconds": e2e_step_s, "plan_cache_hits_rank0": cache_hits, "host_threads": len(groups),
+                    "timeline_last_step_rank0": {"note": "calls of the instances modelled >= 1 ms: entry, plan acquired (cache hit: leaves "
+                                                         "re-read), leaves on the device, run done", "calls": timeline,
+                                                 "step_ms": round(e2e_step_s[-1] * 1e3, 2)},
                     "rank0_per_step": {k: v / e2e_steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(lt.item()), "clocks": clocks, "counts_ok": ok, "instances": n_inst,
             "issue": "sequential" if args.sequential else "async: all of a rank's instances in flight",

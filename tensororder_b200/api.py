@@ -544,7 +544,7 @@ class B200API:
                 "launches": compiled.interruptible_stats["launches"],
                 "h2d_bytes": int(compiled.flat.leaf_data.nbytes), "d2h_bytes": 32,
                 "peak_bytes": compiled.peak_bytes, "slices": total, "rank": rank, "world": world,
-                "plan_cache_hit": hit,
+                "plan_cache_hit": hit, "t_call": (t0, t1, t2, t3),  # perf_counter: entry, plan acquired, leaves on the device, run done
             }
         finally:
             self._done_with(compiled, failed)

@@ -112,7 +112,7 @@ static bool g_configured[64] = {false};  // per device: kernel attributes live i
 // Process-wide caches.  A call of B200API.contract_sliced creates, uploads, runs and destroys a plan;
 // cudaMalloc / cudaMallocHost / cudaFree / stream + event creation cost milliseconds, more than the
 // kernels of a small instance.  Blocks and streams are therefore recycled (device blocks above
-// 2 GiB are returned to the driver at once; at most 8 GiB stay cached per device).
+// 4 GiB are returned to the driver at once; at most 8 GiB stay cached per device).
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct Block { void* ptr; size_t size; int device; bool pinned; };
@@ -120,13 +120,33 @@ struct StreamSet { cudaStream_t stream; cudaEvent_t ev0, ev1; int device; };
 std::mutex g_pool_mu;
 std::vector<Block> g_free_blocks;
 std::vector<StreamSet> g_free_streams;
-const size_t kMaxCachedBlock = (size_t)2 << 30;
+const size_t kMaxCachedBlock = (size_t)4 << 30;
 const size_t kMaxCachedTotal = (size_t)8 << 30;
 const size_t kMaxCachedPinned = (size_t)256 << 20;  // idle pinned host memory kept for reuse
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-void pool_trim_locked(int device, size_t keep_bytes) {
+// cudaFree / cudaFreeHost wait for EVERYTHING in flight on the device, so with several host threads running contractions
+// (the bench's e2e arm, any caller with a thread pool) a free issued under the pool lock stalled every other thread at its next
+// pool call until the GPU drained — measured as 86 -> 263 ms steps.  Rules: (1) nothing is freed on a cache MISS (the old
+// "drop the largest block that was too small" rule), (2) sizes are rounded up to 4 significant bits so plans of similar
+// size exchange blocks instead of missing, (3) blocks over the cap are taken off the list under the lock and freed after it.
+size_t size_class(size_t bytes) {
+    bytes = std::max<size_t>(bytes, 4096);
+    int e = 0;
+    while (((size_t)1 << (e + 1)) <= bytes) e++;
+    const size_t step = (size_t)1 << std::max(e - 3, 12);
+    return align_up(bytes, step);
+}
+
+void free_blocks(const std::vector<Block>& victims) {
+    for (const Block& b : victims) {
+        if (b.pinned) cudaFreeHost(b.ptr); else cudaFree(b.ptr);
+    }
+}
+
+// takes cached device blocks of `device` off the list (largest first) until at most keep_bytes stay; the caller frees them
+void pool_trim_locked(int device, size_t keep_bytes, std::vector<Block>* victims) {
     size_t total = 0;
     for (const Block& b : g_free_blocks)
         if (!b.pinned && b.device == device) total += b.size;
@@ -136,14 +156,14 @@ void pool_trim_locked(int device, size_t keep_bytes) {
             if (!g_free_blocks[i].pinned && g_free_blocks[i].device == device &&
                 (big < 0 || g_free_blocks[i].size > g_free_blocks[big].size)) big = (int)i;
         if (big < 0) break;
-        cudaFree(g_free_blocks[big].ptr);
+        victims->push_back(g_free_blocks[big]);
         total -= g_free_blocks[big].size;
         g_free_blocks.erase(g_free_blocks.begin() + big);
     }
 }
 
 cudaError_t pool_acquire(size_t bytes, int device, bool pinned, Block* out) {
-    bytes = (bytes + 4095) / 4096 * 4096;
+    bytes = size_class(bytes);
     {
         std::lock_guard<std::mutex> lock(g_pool_mu);
         int best = -1;
@@ -152,36 +172,23 @@ cudaError_t pool_acquire(size_t bytes, int device, bool pinned, Block* out) {
             if (b.pinned != pinned || (!pinned && b.device != device) || b.size < bytes) continue;
             if (best < 0 || b.size < g_free_blocks[best].size) best = (int)i;
         }
-        if (best >= 0) {
+        // a cached block up to twice the size is taken as it is; a larger one stays for a plan that needs it
+        if (best >= 0 && g_free_blocks[best].size <= 2 * bytes) {
             *out = g_free_blocks[best];
             g_free_blocks.erase(g_free_blocks.begin() + best);
             return cudaSuccess;
         }
     }
-    // nothing cached fits: allocate with headroom (so a slightly larger plan later still fits) and drop
-    // the largest cached block that was too small, keeping the pool from growing without bound
-    if (bytes < kMaxCachedBlock / 2) bytes = align_up(bytes + bytes / 4, 4096);
-    {
-        std::lock_guard<std::mutex> lock(g_pool_mu);
-        int big = -1;
-        for (size_t i = 0; i < g_free_blocks.size(); i++) {
-            const Block& b = g_free_blocks[i];
-            if (b.pinned != pinned || (!pinned && b.device != device)) continue;
-            if (big < 0 || b.size > g_free_blocks[big].size) big = (int)i;
-        }
-        if (big >= 0) {
-            if (pinned) cudaFreeHost(g_free_blocks[big].ptr); else cudaFree(g_free_blocks[big].ptr);
-            g_free_blocks.erase(g_free_blocks.begin() + big);
-        }
-    }
     void* ptr = nullptr;
     cudaError_t e = pinned ? cudaMallocHost(&ptr, bytes) : cudaMalloc(&ptr, bytes);
-    if (e == cudaErrorMemoryAllocation && !pinned) {
+    if (e == cudaErrorMemoryAllocation && !pinned) {  // out of memory: give everything cached back, then try once more
         cudaGetLastError();
+        std::vector<Block> victims;
         {
             std::lock_guard<std::mutex> lock(g_pool_mu);
-            pool_trim_locked(device, 0);
+            pool_trim_locked(device, 0, &victims);
         }
+        free_blocks(victims);
         e = cudaMalloc(&ptr, bytes);
     }
     if (e != cudaSuccess) return e;
@@ -191,31 +198,32 @@ cudaError_t pool_acquire(size_t bytes, int device, bool pinned, Block* out) {
 
 void pool_release(const Block& b) {
     if (!b.ptr) return;
-    if (!b.pinned && b.size > kMaxCachedBlock) {
-        cudaFree(b.ptr);
-        return;
+    std::vector<Block> victims;
+    if ((!b.pinned && b.size > kMaxCachedBlock) || (b.pinned && b.size > kMaxCachedPinned / 4)) {
+        victims.push_back(b);
+    } else {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        g_free_blocks.push_back(b);
+        if (!b.pinned) {
+            pool_trim_locked(b.device, kMaxCachedTotal, &victims);
+        } else {
+            size_t pinned_total = 0;  // idle pinned blocks: oldest go first once the cap is exceeded
+            for (const Block& f : g_free_blocks)
+                if (f.pinned) pinned_total += f.size;
+            for (size_t i = 0; i < g_free_blocks.size() && pinned_total > kMaxCachedPinned;) {
+                if (!g_free_blocks[i].pinned) { i++; continue; }
+                pinned_total -= g_free_blocks[i].size;
+                victims.push_back(g_free_blocks[i]);
+                g_free_blocks.erase(g_free_blocks.begin() + i);
+            }
+        }
     }
-    if (b.pinned && b.size > kMaxCachedPinned / 4) {
-        cudaFreeHost(b.ptr);
-        return;
-    }
-    std::lock_guard<std::mutex> lock(g_pool_mu);
-    g_free_blocks.push_back(b);
-    if (!b.pinned) {
-        pool_trim_locked(b.device, kMaxCachedTotal);
-        return;
-    }
-    size_t pinned_total = 0;  // idle pinned blocks: oldest go first once the cap is exceeded
-    for (const Block& f : g_free_blocks)
-        if (f.pinned) pinned_total += f.size;
-    for (size_t i = 0; i < g_free_blocks.size() && pinned_total > kMaxCachedPinned;) {
-        if (!g_free_blocks[i].pinned) { i++; continue; }
-        pinned_total -= g_free_blocks[i].size;
-        cudaFreeHost(g_free_blocks[i].ptr);
-        g_free_blocks.erase(g_free_blocks.begin() + i);
-    }
+    free_blocks(victims);
 }
 
+// (Stream priorities by plan size — shortest job first across the contractions several host threads keep in flight — were
+// measured and change nothing: 82.3-83.9 vs 81.9-85.9 ms per e2e bench step; a small plan's kernels cannot co-reside with two
+// 96-register GEMM CTAs per SM either way.  What shortens the step is more host threads: profiles/r02i_e2e_threads.md.)
 cudaError_t streams_acquire(int device, StreamSet* out) {
     {
         std::lock_guard<std::mutex> lock(g_pool_mu);
@@ -683,13 +691,19 @@ int tob_plan_release(tob_plan* p) {
 }
 
 int tob_pool_trim(int32_t device) {
-    std::lock_guard<std::mutex> lock(g_pool_mu);
-    for (size_t i = g_free_blocks.size(); i-- > 0;) {
-        const Block b = g_free_blocks[i];
-        if (device >= 0 && !b.pinned && b.device != device) continue;
+    std::vector<Block> victims;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (size_t i = g_free_blocks.size(); i-- > 0;) {
+            const Block b = g_free_blocks[i];
+            if (device >= 0 && !b.pinned && b.device != device) continue;
+            victims.push_back(b);
+            g_free_blocks.erase(g_free_blocks.begin() + i);
+        }
+    }
+    for (const Block& b : victims) {
         if (!b.pinned) cudaSetDevice(b.device);
         if (b.pinned) cudaFreeHost(b.ptr); else cudaFree(b.ptr);
-        g_free_blocks.erase(g_free_blocks.begin() + i);
     }
     return TOB_OK;
 }
