@@ -474,7 +474,7 @@ def b200_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from tensororder_b200.api import PLAN_CACHE, B200API, CompiledPlan
+    from tensororder_b200.api import PLAN_CACHE, B200API, CollectiveOrder, CompiledPlan
     from tensororder_b200.flatten import flatten_plan
 
     torch.cuda.set_device(local_rank)
@@ -655,33 +655,39 @@ def b200_arm(args, rank, world, local_rank):
     cache_hits = 0
     from concurrent.futures import ThreadPoolExecutor
 
-    def contract_one(it):
+    order = CollectiveOrder()
+
+    def contract_one(it, ticket=None):
         """One instance through the reference-facing call; returns (count, stats)."""
         api = B200API()
         api.add_argument("entry_type", "float64")
         api.add_argument("device", local_rank)
         api.add_argument("distributed", it["owner"] is None)
+        if ticket is not None:
+            api.add_argument("collective_ticket", (order, ticket))
         got = float(api.contract_sliced(plans[it["name"]]))
         # sliced instances come back already all-reduced (identical on every rank): count them once
         return (got / world if it["owner"] is None else got), api.last_stats
 
-    def contract_unsliced(batch):
+    def contract_batch(batch, step):
         torch.cuda.set_device(local_rank)
-        return [contract_one(it) for it in batch]
+        return [contract_one(it, step * len(ordered) + ordered.index(it) if it in ordered else None) for it in batch]
 
     # host threads making the public call: the instances of a step are independent objects, so a user contracts them from
     # a small thread pool (ctypes releases the GIL inside the C ABI; every plan runs on its own streams, so the GPU sees
-    # several contractions at once and one thread's host work hides behind another's device time).  N > 1: the sliced
-    # instances stay on ONE thread — each call ends in an all-reduce that must be issued in the same order on every rank —
-    # and the rank's unsliced instances go to a second one.  N = 1: no collective, four threads (longest-first packing: one per sliced instance, one for the small ones).
-    if world > 1:
-        groups = [[it for it in mine if it["owner"] is None], [it for it in mine if it["owner"] is not None]]
-    else:
-        groups, gload = [[] for _ in range(E2E_THREADS)], [0.0] * E2E_THREADS
-        for it in sorted(mine, key=lambda x: -x["model_s"]):
-            g = min(range(E2E_THREADS), key=lambda q: gload[q])
-            groups[g].append(it)
-            gload[g] += it["model_s"]
+    # several contractions at once and one thread's host work hides behind another's device time).  Instances whose call
+    # ends in an all-reduce (N > 1: the sliced ones) get a thread each and a collective ticket (api.CollectiveOrder): they
+    # run concurrently on the device and their all-reduces are issued in ticket order on every rank; everything else is
+    # packed longest-first over the remaining threads (profiles/r02i_e2e_threads.md).
+    ordered = [it for it in mine if world > 1 and it["owner"] is None]
+    free = [it for it in mine if it not in ordered]
+    n_free = max(1, E2E_THREADS - len(ordered))
+    packs, pload = [[] for _ in range(n_free)], [0.0] * n_free
+    for it in sorted(free, key=lambda x: -x["model_s"]):
+        g = min(range(n_free), key=lambda q: pload[q])
+        packs[g].append(it)
+        pload[g] += it["model_s"]
+    groups = [[it] for it in ordered] + packs
     groups = [g for g in groups if g] or [[]]
     pool = ThreadPoolExecutor(max_workers=max(1, len(groups) - 1))
     for step in range(1 + e2e_steps):  # one warm-up pass (pays the plan compiles: cached by plan identity afterwards)
@@ -689,8 +695,8 @@ def b200_arm(args, rank, world, local_rank):
         t0 = time.perf_counter()
         host = np.zeros(n_inst)
         h2d = d2h = 0
-        side = [pool.submit(contract_unsliced, g) for g in groups[1:]]
-        results = [(it, contract_one(it)) for it in groups[0]]
+        side = [pool.submit(contract_batch, g, step) for g in groups[1:]]
+        results = list(zip(groups[0], contract_batch(groups[0], step)))
         for g, fut in zip(groups[1:], side):
             results += list(zip(g, fut.result()))
         timeline = [{"n": it["n"], "thread": next(gi for gi, g in enumerate(groups) if it in g),

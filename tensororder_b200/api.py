@@ -369,6 +369,31 @@ class PlanCache:
 PLAN_CACHE = PlanCache()
 
 
+class CollectiveOrder:
+    """Turnstile for host threads whose `contract_sliced` calls end in a collective.  Under `torch.distributed` every
+    rank must issue the count all-reduces of concurrent contractions in the same order; threads do not.  The caller gives
+    each call a ticket (the same numbering on every rank: `api.add_argument("collective_ticket", (order, k))`), the
+    contractions run concurrently on the device, and the all-reduces pass the turnstile in ticket order 0, 1, 2, ...
+    A call that fails before its collective (an invalid plan: the same on every rank) gives its ticket up the same way."""
+
+    def __init__(self, first: int = 0):
+        self._cond = threading.Condition()
+        self._next = int(first)
+
+    def enter(self, ticket: int) -> None:
+        with self._cond:
+            if ticket < self._next:
+                raise ValueError("collective ticket %d was already served (next is %d)" % (ticket, self._next))
+            while self._next != ticket:
+                self._cond.wait()
+
+    def leave(self, ticket: int) -> None:
+        with self._cond:
+            if self._next == ticket:
+                self._next = ticket + 1
+            self._cond.notify_all()
+
+
 class B200API:
     """Drop-in for `tensor_network.ALL_APIS[...]` entries (src/tensor_network/__init__.py:12-16).
 
@@ -397,6 +422,7 @@ class B200API:
         self._lanes = 0
         self._branches = 0
         self._distributed = True
+        self._ticket = None  # (CollectiveOrder, k): one-shot, consumed by the next contract_sliced call
         self._mem_limit_bytes = 0
         self._plan_cache = True
         self.last_stats = {}
@@ -429,6 +455,10 @@ class B200API:
             self._microtree = bool(value)
         elif key == "distributed":
             self._distributed = bool(value)
+        elif key == "collective_ticket":
+            if value is not None and not (isinstance(value, tuple) and len(value) == 2 and isinstance(value[0], CollectiveOrder)):
+                raise ValueError("collective_ticket takes (CollectiveOrder, int)")
+            self._ticket = value
         elif key == "mem_limit_bytes":
             self._mem_limit_bytes = int(value)  # plans needing more raise OutOfMemoryError (=> slice once more)
         elif key == "plan_cache":
@@ -509,8 +539,25 @@ class B200API:
 
     # ---- the primary entry (base_api.py:17-28, called from execution.py:136) ----
     def contract_sliced(self, execution_plan, num_slice_limit=None):
+        ticket, self._ticket = self._ticket, None
+        served = [False]
+        try:
+            return self._contract_sliced(execution_plan, num_slice_limit, ticket, served)
+        finally:
+            if ticket is not None and not served[0]:  # failed before its collective: give the ticket up
+                ticket[0].enter(ticket[1])
+                ticket[0].leave(ticket[1])
+
+    def _contract_sliced(self, execution_plan, num_slice_limit, ticket, served):
         if self._entry_type in ("bigint", "int", "uint"):
-            exact = self._contract_exact(execution_plan, num_slice_limit)
+            if ticket is not None:  # several collectives per call (one per prime): the whole call holds the turnstile
+                ticket[0].enter(ticket[1])
+                served[0] = True
+            try:
+                exact = self._contract_exact(execution_plan, num_slice_limit)
+            finally:
+                if ticket is not None:
+                    ticket[0].leave(ticket[1])
             if self._entry_type == "bigint":
                 return exact
             wrapped = exact % (1 << 64)  # numpy's integer arithmetic wraps modulo 2^64
@@ -536,7 +583,17 @@ class B200API:
                 error = self._give_up_if_unsliceable(exc, compiled)
                 t2 = time.perf_counter()
             t3 = time.perf_counter()
-            result = self._combine(partial, error) if world > 1 else self._raise_or(partial, error)
+            if world > 1:
+                if ticket is not None:
+                    ticket[0].enter(ticket[1])
+                    served[0] = True
+                try:
+                    result = self._combine(partial, error)
+                finally:
+                    if ticket is not None:
+                        ticket[0].leave(ticket[1])
+            else:
+                result = self._raise_or(partial, error)
             failed = False
             self.last_stats = {
                 "flatten_compile_s": t1 - t0, "upload_s": t2 - t1, "run_s": t3 - t2,

@@ -117,3 +117,72 @@ def test_a_failure_on_one_rank_is_raised_on_every_rank(kind):
         for entry_type in ("float64", "bigint"):
             assert out[(rank, entry_type)] == kind, (rank, entry_type, dict(out))
         assert out[(rank, "after")] == 2802717837.0
+
+
+def _threaded_worker(rank, world, port, out):
+    """Three host threads per rank, each contracting a different sliced plan; the threads reach their all-reduce in a
+    DIFFERENT order on the two ranks (staggered sleeps).  Tickets keep the collectives paired."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import threading
+    import time
+
+    import torch.distributed as dist
+
+    from conftest import load_golden
+    from program_sim import install_fake_device
+    from tensororder_b200 import api as api_mod
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    install_fake_device(api_mod.CompiledPlan)
+    jobs = [("vc50_lineflow", "min3"), ("vc50_mcc_lineflow", "min3"), ("vc50_lineflow", "min3")]
+    plans = [load_golden(n).variant(v).as_execution_plan() for n, v in jobs]
+    order = api_mod.CollectiveOrder()
+    results = {}
+
+    def call(i, ticket):
+        time.sleep(0.05 * (i if rank == 0 else (2 - i)))  # rank 0 arrives 0,1,2 — rank 1 arrives 2,1,0
+        api = api_mod.B200API()
+        api.add_argument("entry_type", "float64")
+        api.add_argument("collective_ticket", (order, ticket))
+        results[ticket] = float(api.contract_sliced(plans[i]))
+
+    for step in range(2):
+        threads = [threading.Thread(target=call, args=(i, 3 * step + i)) for i in range(3)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+            assert not t.is_alive(), "deadlock at the collective turnstile"
+    # a call that fails before its collective (the same way on every rank) gives its ticket up; the next one still runs
+    api = api_mod.B200API()
+    api.add_argument("entry_type", "float64")
+    api.add_argument("collective_ticket", (order, 6))
+    try:
+        api.contract_sliced(object())
+        results["bad"] = "no error"
+    except Exception:  # noqa: BLE001
+        results["bad"] = "raised"
+    api.add_argument("collective_ticket", (order, 7))
+    results[7] = float(api.contract_sliced(plans[0]))
+    out[rank] = dict(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_threads_with_collective_tickets_stay_paired_across_ranks():
+    sys.path.insert(0, HERE)
+    from conftest import load_golden
+
+    want = [load_golden(n).variant("min3").expected["count"] for n in ("vc50_lineflow", "vc50_mcc_lineflow", "vc50_lineflow")]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_threaded_worker, args=(2, port, out), nprocs=2, join=True)
+    for rank in range(2):
+        res = out[rank]
+        for ticket in range(6):
+            assert math.isclose(res[ticket], want[ticket % 3], rel_tol=1e-12), (rank, ticket, res)
+        assert res["bad"] == "raised" and math.isclose(res[7], want[0], rel_tol=1e-12)
