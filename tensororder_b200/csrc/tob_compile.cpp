@@ -63,6 +63,7 @@ Tuning& tuning() {
         x.streamk = TOB_TUNE_STREAMK;
         x.streamk_min_tiles_log2 = TOB_TUNE_STREAMK_MIN_TILES_LOG2;
         x.streamk_max_tiles_log2 = TOB_TUNE_STREAMK_MAX_TILES_LOG2;
+        x.streamk_max_steps = TOB_TUNE_STREAMK_MAX_STEPS;
         x.store_tile = TOB_TUNE_STORE_TILE;
         x.permute_low_bits = 0;
         x.permute_ctas_per_sm = 0;
@@ -88,7 +89,7 @@ const TuneField kTuneFields[] = {
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
     {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
-    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"store_tile", &Tuning::store_tile, nullptr},
+    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"streamk_max_steps", &Tuning::streamk_max_steps, nullptr}, {"store_tile", &Tuning::store_tile, nullptr},
     {"permute_low_bits", &Tuning::permute_low_bits, nullptr}, {"permute_ctas_per_sm", &Tuning::permute_ctas_per_sm, nullptr},
     {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };
@@ -151,7 +152,10 @@ double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c) 
 // 128x64 tiles, K >= 256 (the warp-specialised pipeline), 64..256 tiles: fewer and an owner sums too many partials (32
 // tiles: 9 each, measured 6 % slower than split-K); more and the one-tile-per-CTA grid is already balanced by the block
 // scheduler while stream-K ranges spread over the whole tile space lose the raster's L2 locality (512 tiles: 13-25 %
-// slower, 1024+: 25-40 % — profiles/r02h_kernel_lab_streamk.md).
+// slower, 1024+: 25-40 % — profiles/r02h_kernel_lab_streamk.md).  And only up to streamk_max_steps K steps per CTA: with a long
+// K the one-tile-per-CTA grid reaches 0.94-0.96 on its own (an SM left with one CTA runs it at the full rate, and the
+// DMMA rate of the busy SMs rises ~10 % once others idle: 1.97 instead of 2.19 us per K step, the chip is power-limited at
+// full FP64 load), so the exchange only costs (m=11,n=10: k=10 +7 %, k=11 +9 %, k=12 0, k=13 -0.7 %).
 double streamk_time_model_us(int m, int n, int k, int* ctas) {
     const Tuning& T = tuning();
     if (m < 7 || n < 6 || k < 8) return -1.0;
@@ -162,7 +166,7 @@ double streamk_time_model_us(int m, int n, int k, int* ctas) {
     const double G = std::ldexp(1.0, tiles_log2 + k - 4), KT = std::ldexp(1.0, k - 4);
     if (G < slots) return -1.0;
     const double steps = std::ceil(G / slots);
-    if (steps / KT + 2.0 > kSkMaxSegs) return -1.0;
+    if (steps / KT + 2.0 > kSkMaxSegs || steps > T.streamk_max_steps) return -1.0;
     if (ctas) *ctas = (int)slots;
     const double step_shared = 2.0 * std::ldexp(1.0, 7 + 6 + 4) / (T.sm_gflops * 1e3 / 2.0);
     return steps * step_shared + T.gemm_fix_us + T.streamk_fix_us;

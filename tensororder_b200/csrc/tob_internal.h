@@ -135,6 +135,7 @@ struct Tuning {
     int streamk;            // 0: never, 1: where the time model says so, 2: experiments only — every eligible GEMM
     int streamk_min_tiles_log2;  // stream-K needs at least this many tiles (few tiles => many partials per owner)
     int streamk_max_tiles_log2;  // ... and at most this many (ranges over several tiles lose the L2 locality of the raster)
+    int streamk_max_steps;       // ... and at most this many K steps per CTA (long K: the one-tile-per-CTA grid is as fast)
     double streamk_fix_us;  // modelled cost of the partial-tile exchange
     int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
     int permute_low_bits, permute_ctas_per_sm;  // stand-alone permutation kernel: tile shape / grid (0 = defaults)

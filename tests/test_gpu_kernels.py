@@ -135,7 +135,7 @@ def tuning():
 
 
 # stream-K forced on every eligible join (the table restricts it to 64..256 tiles)
-SK = {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40}
+SK = {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40, "streamk_max_steps": 1 << 30}
 
 VARIANT_CASES = [
     # long-K joins (K >= 256 per split) on the warp-specialised kernel under forced splits, swapped operands

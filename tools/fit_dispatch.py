@@ -47,7 +47,7 @@ def tget(key):
 KEYS = ["gemm_min_free", "gemm_min_k", "gemm_smallk_min_free", "t1_max_k", "t1_small_out", "t1_small_max_k",
         "t32_max_k", "t32_min_out", "persist_max_k", "sm_gflops", "alone_frac", "gemm_fix_us", "reduce_gbs",
         "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2", "streamk", "streamk_min_tiles_log2",
-        "streamk_max_tiles_log2", "streamk_fix_us", "store_tile"] + ["gemm_min_out.%d" % i for i in range(17)]
+        "streamk_max_tiles_log2", "streamk_max_steps", "streamk_fix_us", "store_tile"] + ["gemm_min_out.%d" % i for i in range(17)]
 for k_ in KEYS:
     DEFAULTS[k_] = tget(k_)
 
@@ -244,17 +244,18 @@ persist_max_k = max([r["k"] for r in persist if r["persistent_us"] <= r["one_til
 sk_rows = []
 for tl in range(4, 11):  # 16 .. 1024 tiles of 128x64
     m, n = 7 + (tl + 1) // 2, 6 + tl // 2
-    for k in (10, 12):
+    for k in (10, 11, 12, 13):
         if m + n + k > 34:
             continue
         tset("streamk", 0)
         dp_us, _ = time_join(m, n, k)
-        tset("streamk", 2); tset("streamk_min_tiles_log2", 0); tset("streamk_max_tiles_log2", 40)
+        tset("streamk", 2); tset("streamk_min_tiles_log2", 0); tset("streamk_max_tiles_log2", 40); tset("streamk_max_steps", 1 << 30)
         sk_us, _ = time_join(m, n, k)
         restore()
         steps = math.ceil((1 << (tl + k - 4)) / 296.0)
         fix = sk_us - steps * (2.0 * 2 ** 17 / (DEFAULTS["sm_gflops"] * 1e3 / 2.0)) - DEFAULTS["gemm_fix_us"]
-        sk_rows.append({"m": m, "n": n, "k": k, "tiles_log2": tl, "best_split_us": dp_us, "streamk_us": sk_us, "residual_fix_us": fix})
+        sk_rows.append({"m": m, "n": n, "k": k, "tiles_log2": tl, "steps_per_cta": steps, "best_split_us": dp_us, "streamk_us": sk_us,
+                        "residual_fix_us": fix})
         print("  stream-K m=%d n=%d k=%d (%d tiles): best split %.1f us, stream-K %.1f us" % (m, n, k, 1 << tl, dp_us, sk_us))
 out["streamk"] = sk_rows
 # the range: from the first to the last tile count where stream-K wins by >= 3 % at some K, as long as it is no worse than
@@ -268,6 +269,9 @@ while wins and not all(t in tie_or_win for t in range(sk_min, sk_max + 1)):
     sk_max -= 1
 win_fix = [r["residual_fix_us"] for r in sk_rows if sk_min <= r["tiles_log2"] <= sk_max and r["streamk_us"] < 0.97 * r["best_split_us"]]
 sk_fix = int(math.ceil(min(win_fix))) if win_fix else int(DEFAULTS["streamk_fix_us"])
+# K steps per CTA up to which it still wins (long K: the one-tile-per-CTA grid catches up), as the next power of two
+win_steps = [r["steps_per_cta"] for r in sk_rows if sk_min <= r["tiles_log2"] <= sk_max and r["streamk_us"] < 0.97 * r["best_split_us"]]
+sk_steps = 1 << int(math.ceil(math.log2(max(win_steps)))) if win_steps else int(DEFAULTS["streamk_max_steps"])
 store = {}
 for v in (0, 1):
     tset("store_tile", v)
@@ -288,7 +292,7 @@ table = {
     "GEMM_FIX_US": float(fit["gemm_fix_us"]), "REDUCE_GBS": float(fit["reduce_gbs"]), "REDUCE_FIX_US": float(fit["reduce_fix_us"]),
     "MAX_KSPLIT_LOG2": int(DEFAULTS["max_ksplit_log2"]), "MIN_K_PER_SPLIT_LOG2": int(DEFAULTS["min_k_per_split_log2"]),
     "STREAMK": 1 if wins else 0, "STREAMK_MIN_TILES_LOG2": sk_min if wins else int(DEFAULTS["streamk_min_tiles_log2"]),
-    "STREAMK_MAX_TILES_LOG2": sk_max if wins else int(DEFAULTS["streamk_max_tiles_log2"]), "STREAMK_FIX_US": sk_fix,
+    "STREAMK_MAX_TILES_LOG2": sk_max if wins else int(DEFAULTS["streamk_max_tiles_log2"]), "STREAMK_FIX_US": sk_fix, "STREAMK_MAX_STEPS": sk_steps,
     "STORE_TILE": store_tile,
 }
 out["table"] = table

@@ -21,7 +21,7 @@ def tset(**kv):
 
 
 DEFAULTS = {}
-for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "store_group_log2", "store_tile", "force_ksplit_log2", "persist_max_k"):
+for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "streamk_max_steps", "store_group_log2", "store_tile", "force_ksplit_log2", "persist_max_k"):
     v = ctypes.c_double()
     assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0
     DEFAULTS[key] = v.value
@@ -90,6 +90,14 @@ def report(m, n, k, label, single, b2b):
 rows = []
 print("| m | n | k | variant | bound | single-launch us | frac | back-to-back us | frac |")
 print("|---|---|---|---|---|---|---|---|---|")
+if what == "streamk_long":
+    for (m, n, k) in [(11, 10, 11), (11, 10, 12), (11, 10, 13), (11, 10, 14), (11, 9, 13), (10, 10, 13), (10, 9, 13), (11, 8, 12), (11, 8, 10)]:
+        reps = 5
+        s0, b0, ref = time_join(m, n, k, {"streamk": 0}, reps)
+        rows.append(report(m, n, k, "data-parallel / split-K", s0, b0))
+        s1, b1, out = time_join(m, n, k, {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40, "streamk_max_steps": 1 << 30}, reps)
+        assert float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max()) < 1e-12
+        rows.append(report(m, n, k, "stream-K", s1, b1))
 if what in ("streamk", "all"):
     shapes = [(11, 10, 10), (11, 10, 9), (10, 10, 10), (10, 10, 8), (11, 11, 8), (11, 11, 10), (11, 11, 12), (12, 11, 10), (12, 12, 8),
               (12, 12, 11), (13, 11, 11), (10, 10, 12), (10, 9, 12), (9, 9, 12), (9, 9, 14), (8, 8, 12), (7, 7, 16), (8, 8, 16), (6, 6, 16)]
@@ -97,7 +105,7 @@ if what in ("streamk", "all"):
         reps = 20 if m + n + k <= 32 else 5
         s0, b0, ref = time_join(m, n, k, {"streamk": 0}, reps)
         rows.append(report(m, n, k, "data-parallel / split-K", s0, b0))
-        s1, b1, out = time_join(m, n, k, {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40}, reps)
+        s1, b1, out = time_join(m, n, k, {"streamk": 2, "streamk_min_tiles_log2": 0, "streamk_max_tiles_log2": 40, "streamk_max_steps": 1 << 30}, reps)
         err = float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max())
         assert err < 1e-12, (m, n, k, err)
         rows.append(report(m, n, k, "stream-K", s1, b1))
