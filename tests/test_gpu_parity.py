@@ -308,3 +308,34 @@ def test_count_is_multilinear_in_a_variable_weight(name, variant):
         if picked == 2:
             break
     assert picked == 2
+
+
+def test_host_threads_contract_concurrently():
+    """Eight host threads, three rounds, instances of every size class through the public call at once (the bench's e2e
+    arm): plans on their own streams, the shared block / stream pools, the plan cache, stream-K flag blocks of concurrent
+    plans.  Every count must match and repeat bit for bit; a stalled pool shows up as the timeout."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = [("vc200_lineflow", "min3"), ("vc150_mcc_factorflow", None), ("vc190_lineflow", None), ("vc180_lineflow", None),
+            ("vc160_lineflow", None), ("vc150_lineflow", "min4"), ("vc120_lineflow", None), ("vc100_lineflow", "min4"),
+            ("vc50_lineflow", None), ("vc50_mcc_lineflow", "min3"), ("vc170_lineflow", None), ("vc140_lineflow", None)]
+    plans, want = [], []
+    for name, variant in jobs:
+        pp = load_golden(name)
+        if variant:
+            pp = pp.variant(variant)
+        plans.append(pp.as_execution_plan())
+        want.append(pp.expected.get("count", load_golden(name).expected.get("count")))
+
+    def call(i):
+        return float(_api().contract_sliced(plans[i]))
+
+    first = None
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        for _ in range(3):
+            got = list(pool.map(call, range(len(jobs)), timeout=120))
+            for g, w, job in zip(got, want, jobs):
+                assert math.isclose(g, w, rel_tol=REL), (job, g, w)
+            if first is None:
+                first = got
+            assert [x.hex() for x in got] == [x.hex() for x in first]
