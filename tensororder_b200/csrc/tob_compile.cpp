@@ -153,9 +153,9 @@ double gemm_time_model_us(int m, int n, int k, int tm_log2, int tn_log2, int c) 
 // tiles: 9 each, measured 6 % slower than split-K); more and the one-tile-per-CTA grid is already balanced by the block
 // scheduler while stream-K ranges spread over the whole tile space lose the raster's L2 locality (512 tiles: 13-25 %
 // slower, 1024+: 25-40 % — profiles/r02h_kernel_lab_streamk.md).  And only up to streamk_max_steps K steps per CTA: with a long
-// K the one-tile-per-CTA grid reaches 0.94-0.96 on its own (an SM left with one CTA runs it at the full rate, and the
-// DMMA rate of the busy SMs rises ~10 % once others idle: 1.97 instead of 2.19 us per K step, the chip is power-limited at
-// full FP64 load), so the exchange only costs (m=11,n=10: k=10 +7 %, k=11 +9 %, k=12 0, k=13 -0.7 %).
+// K a power-of-two split of the one-tile-per-CTA grid balances just as well — its partials' round trip and reduce pass are
+// amortised over the long K — and the exchange buys nothing (m=11,n=10: k=10 +7 %, k=11 +9 %, k=12 0, k=13 -0.7 %;
+// profiles/r02i_kernel_lab_streamk_long.md).
 double streamk_time_model_us(int m, int n, int k, int* ctas) {
     const Tuning& T = tuning();
     if (m < 7 || n < 6 || k < 8) return -1.0;
