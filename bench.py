@@ -417,7 +417,9 @@ def extra_rank_sweep(torch, dev, hbm_gbs, fp64_peak):
         aa = np.arange(ra - k, ra, dtype=np.int32)
         ab = np.arange(rb - k, rb, dtype=np.int32)
         best = None
-        for rep in range(4):
+        # a freshly allocated multi-GB output needs ~6 full passes before its writes run at speed (measured: m=n=15,k=4 takes
+        # 2.16 ms for its first five launches, 1.47 ms from then on and on any re-used buffer; profiles/r02i_first_touch.md)
+        for rep in range(10 if T >= 32 else 4):
             ms = (ctypes.c_float * 3)()
             torch.cuda.synchronize(dev)
             rc_ = cabi.lib.tob_tensordot_device(a.data_ptr(), ra, b.data_ptr(), rb, aa.ctypes.data_as(P32),
@@ -462,7 +464,7 @@ def extra_rank_sweep(torch, dev, hbm_gbs, fp64_peak):
         del a, b, c, ws
         torch.cuda.empty_cache()
     return {"config": "BASELINE config 5 digest: single contractions, T total / k contracted indices, GEMM-ready operands",
-            "timing": "ms / frac: ONE launch between two CUDA events (best of 3); ms_back_to_back / frac_back_to_back: the same "
+            "timing": "ms / frac: ONE launch between two CUDA events (best of 3, of 9 for T >= 32); ms_back_to_back / frac_back_to_back: the same "
                       "launch repeated inside one CUDA graph, replay time / repetitions (operands of T <= 30 stay in the 126 MB L2 "
                       "either way, as they do behind their producer in a tree)",
             "points": rows}
