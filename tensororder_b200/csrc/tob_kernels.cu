@@ -1152,8 +1152,16 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_s
             const unsigned long long s0 = (unsigned long long)tile << (k - 4);
             const int first = (int)(s0 < r * (q + 1) ? s0 / (q + 1) : r + (s0 - r * (q + 1)) / q);
             for (int j = first; j < rank; j++) {
-                if (lane == 0)
-                    while (ld_acquire_u32(flags + 1 + j) == 0u) __nanosleep(64);
+                if (lane == 0) {
+                    // the contributor is resident and publishes before it waits for anyone, so this ends within its open
+                    // segment's run time (microseconds); seconds of spinning mean a broken invariant: fail the launch
+                    // (the host sees a CUDA error) instead of hanging the device
+                    unsigned spins = 0;
+                    while (ld_acquire_u32(flags + 1 + j) == 0u) {
+                        __nanosleep(128);
+                        if (++spins > (1u << 25)) __trap();
+                    }
+                }
                 __syncwarp();
                 const double2* theirs = slots + (size_t)j * (MB * NB * NC) + tid;
 #pragma unroll
