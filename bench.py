@@ -106,8 +106,22 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []   # (sm MHz, max sm MHz, throttle-reason bitmask, watts) through NVML, every 20 ms
+        self.stop_flag = False
 
     def start(self):
+        try:  # NVML in-process: ~50 samples per second instead of nvidia-smi's 5
+            import pynvml
+
+            pynvml.nvmlInit()
+            cuda_visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(cuda_visible.split(",")[self.gpu]) if cuda_visible and cuda_visible.split(",")[self.gpu].isdigit() else self.gpu
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -116,11 +130,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), smax,
+                                     nv.nvmlDeviceGetCurrentClocksThrottleReasons(h), nv.nvmlDeviceGetPowerUsage(h) / 1e3))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            nv = self.nvml[0]
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            sm = sorted(x[0] for x in self.samples)
+            load = sm[len(sm) // 2:] if sm else []  # upper half: idle gaps between steps pull the clock down
+            reasons = sorted({name for x in self.samples for name, bit in names if x[2] & bit})
+            return {"sm_mhz": (float(load[len(load) // 2]) if load else None), "sm_min_mhz": (float(sm[0]) if sm else None),
+                    "sm_max_mhz": (float(max(x[1] for x in self.samples)) if self.samples else None), "reasons": reasons,
+                    "samples": len(sm), "power_w_max": (max(x[3] for x in self.samples) if self.samples else None), "source": "nvml, 20 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -141,7 +177,7 @@ class ClockSampler:
         # median of the samples taken under load (upper half: idle gaps between steps pull the clock down)
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(smax) if smax else None),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi, 200 ms"}
 
 
 # --------------------------------------------------------------------------------------------------
