@@ -628,14 +628,15 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
 // instead of overlapping; here both are fed all the time.  The B fragments of the whole K step stay in registers
 // (NB x 4 doubles), the accumulators shrink from 64 to 16 * RP registers.
 // ------------------------------------------------------------------------------------------------
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int RP>
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int RP, int KS = 1>
 __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NT = WM * WN * 32;
     constexpr int WTM = TM / WM, WTN = TN / WN;
     constexpr int MB = WTM / 8, NB = WTN / 8;
-    constexpr int TK = 16, LDS = TK + 4, CHUNKS = TK / 2, RPP = NT / CHUNKS, K4 = TK / 4;
-    static_assert(TM % RPP == 0 && TN % RPP == 0 && MB % RP == 0, "loader passes / row groups");
+    // KS = 2: K = 32, both K steps of a tile resident in one stage; the B fragments are then re-read per row group and K step
+    constexpr int TK = 16 * KS, LDS = TK + 4, CHUNKS = TK / 2, RPP = NT / CHUNKS, K4 = 4;
+    static_assert(TM % RPP == 0 && TN % RPP == 0 && MB % RP == 0 && (KS == 1 || KS == 2), "loader passes / row groups");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + STAGES * TM * LDS;
@@ -655,8 +656,8 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) 
     const unsigned long long total = tiles << ks;
     const int group_log2 = (p.m - TM_LOG2) < p.raster_group_log2 ? (p.m - TM_LOG2) : p.raster_group_log2;
     const int pg_log2 = group_log2 + (p.n - TN_LOG2);
-    const unsigned long long Ksplit = (1ull << k) >> ks;   // <= TK
-    const int k4_end = (int)((Ksplit + 3) / 4);
+    const unsigned long long Ksplit = (1ull << k) >> ks;   // <= TK (== TK when KS == 2)
+    const int k4_end = KS == 1 ? (int)((Ksplit + 3) / 4) : K4;
     const long long nmine = total > blockIdx.x ? (long long)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
     const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
@@ -721,28 +722,40 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) 
         double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
         const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
         double bf[NB][K4];
+        if (KS == 1) {
 #pragma unroll
-        for (int j = 0; j < NB; j++)
+            for (int j = 0; j < NB; j++)
 #pragma unroll
-            for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = (k4 < k4_end) ? bs[j * 8 * LDS + k4 * 4] : 0.0;
+                for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = (k4 < k4_end) ? bs[j * 8 * LDS + k4 * 4] : 0.0;
+        }
 #pragma unroll
         for (int i0 = 0; i0 < MB; i0 += RP) {
             double acc[RP][NB][2];
-            double af[RP][K4];
 #pragma unroll
-            for (int r = 0; r < RP; r++) {
-#pragma unroll
-                for (int k4 = 0; k4 < K4; k4++) af[r][k4] = (k4 < k4_end) ? as[(i0 + r) * 8 * LDS + k4 * 4] : 0.0;
+            for (int r = 0; r < RP; r++)
 #pragma unroll
                 for (int j = 0; j < NB; j++) acc[r][j][0] = acc[r][j][1] = 0.0;
-            }
 #pragma unroll
-            for (int k4 = 0; k4 < K4; k4++) {
-                if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
+            for (int h = 0; h < KS; h++) {
+                double af[RP][K4];
 #pragma unroll
                 for (int r = 0; r < RP; r++)
 #pragma unroll
-                    for (int j = 0; j < NB; j++) dmma884(acc[r][j][0], acc[r][j][1], af[r][k4], bf[j][k4]);
+                    for (int k4 = 0; k4 < K4; k4++) af[r][k4] = (k4 < k4_end) ? as[(i0 + r) * 8 * LDS + h * 16 + k4 * 4] : 0.0;
+                if (KS > 1) {
+#pragma unroll
+                    for (int j = 0; j < NB; j++)
+#pragma unroll
+                        for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = bs[j * 8 * LDS + h * 16 + k4 * 4];
+                }
+#pragma unroll
+                for (int k4 = 0; k4 < K4; k4++) {
+                    if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
+#pragma unroll
+                    for (int r = 0; r < RP; r++)
+#pragma unroll
+                        for (int j = 0; j < NB; j++) dmma884(acc[r][j][0], acc[r][j][1], af[r][k4], bf[j][k4]);
+                }
             }
             unsigned long long rb[RP];
 #pragma unroll
@@ -1228,6 +1241,7 @@ constexpr size_t gemm_smem_bytes() {
 // three CTAs per SM at 80 registers (0.80), stores deferred behind the next group's DMMAs (0.83), 64x64 tiles at four
 // CTAs per SM on k_gemm_dmma_p (0.83, and 0.73 instead of 0.72 of the FP64 peak at k = 5).
 #define GEMM_76_P1 k_gemm_dmma_p1<7, 6, 4, 2, 3, 2, 2>
+#define GEMM_76_P2 k_gemm_dmma_p1<7, 6, 4, 2, 2, 2, 2, 2>   // K = 32: two K steps per stage, two stages (three do not fit twice per SM)
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 #define GEMM_76_SK k_gemm_dmma_sk<7, 6, 4, 2, 4, 2, 2>
@@ -1249,6 +1263,8 @@ cudaError_t configure_kernels() {
     e = cudaFuncSetAttribute(GEMM_76_P, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_P1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(GEMM_76_P2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 32, 2>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
@@ -1536,14 +1552,20 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
         } else if (op.tm_log2 == 7 && op.tn_log2 == 6) {
             const Tuning& T = tuning();
             const int kk = op.k - op.ksplit_log2;  // log2 of the K range one CTA walks
-            if (kk <= T.persist_max_k && blocks > 2ull * (unsigned long long)num_sms())
+            if (kk == 5 && T.store_tile == 2 && blocks >= 2048) {
+                // K = 32, >= 2048 tiles (tensor time 1.5x the store time): the row-streamed persistent kernel with both K steps
+                // resident: 0.72 -> 0.79 of the FP64 peak at m=15,n=14; at 1024 tiles the one-tile-per-CTA kernel is 4 % faster
+                KParams pp = p;
+                pp.raster_group_log2 = T.store_group_log2;
+                GEMM_76_P2<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 32, 2>(), stream>>>(pp);
+            } else if (kk <= T.persist_max_k && blocks > 2ull * (unsigned long long)num_sms())
                 // short K, more tiles than CTA slots (the store-bound joins): persistent CTAs prefetch the next tiles
                 // (a shared-memory-staged epilogue writing 512-byte runs was measured in round 2 and is 25-30 % SLOWER than
                 // the direct 16-byte scatter: profiles/r02b_kernel_lab_tma_staged.md — its barriers serialise the tile)
             {
                 KParams pp = p;
                 pp.raster_group_log2 = T.store_group_log2;  // raster order of the persistent tile walk
-                if (T.store_tile == 1 && kk == 4)
+                if (T.store_tile >= 1 && kk == 4)
                     // K = 16 (the DMMA time is 3/4 of the store time): rows leave while the next rows compute, 0.78 -> 0.89 of HBM
                     GEMM_76_P1<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(pp);
                 else

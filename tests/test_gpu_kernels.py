@@ -152,6 +152,8 @@ VARIANT_CASES = [
     ({"store_group_log2": 0}, (16, 14, 4)), ({"store_group_log2": 2}, (17, 15, 5)),
     # K = 16: the row-streamed persistent kernel (table default) under a forced split, and the whole-tile kernel it replaced
     ({"force_ksplit_log2": 1}, (20, 19, 5)), ({"store_tile": 0}, (16, 14, 4)), ({"store_tile": 1}, (14, 17, 4)),
+    # K = 32 on the row-streamed kernel (2048 tiles and more), under a forced split, and switched off
+    ({"store_tile": 2}, (18, 17, 5)), ({"store_tile": 2, "force_ksplit_log2": 1}, (19, 17, 6)), ({"store_tile": 1}, (18, 17, 5)),
 ]
 
 

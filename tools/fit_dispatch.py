@@ -273,13 +273,17 @@ sk_fix = int(math.ceil(min(win_fix))) if win_fix else int(DEFAULTS["streamk_fix_
 win_steps = [r["steps_per_cta"] for r in sk_rows if sk_min <= r["tiles_log2"] <= sk_max and r["streamk_us"] < 0.97 * r["best_split_us"]]
 sk_steps = 1 << int(math.ceil(math.log2(max(win_steps)))) if win_steps else int(DEFAULTS["streamk_max_steps"])
 store = {}
-for v in (0, 1):
+for v in (0, 1, 2):  # 0: whole tile then stores; 1: rows streamed at K = 16; 2: also at K = 32 (>= 2048 tiles)
     tset("store_tile", v)
-    store[v] = [time_join(m, n, 4)[0] for (m, n) in ((14, 14), (15, 14), (13, 12))]
+    store[v] = {"k4": [time_join(m, n, 4)[0] for (m, n) in ((14, 14), (15, 14), (13, 12))],
+                "k5": [time_join(m, n, 5)[0] for (m, n) in ((15, 14), (14, 12), (13, 11))]}
     restore()
 out["store_tile"] = store
-store_tile = 1 if sum(store[1]) < sum(store[0]) else 0
-print("  K = 16 store kernel: whole tile %s us, row-streamed %s us" % (["%.1f" % x for x in store[0]], ["%.1f" % x for x in store[1]]))
+store_tile = 0
+if sum(store[1]["k4"]) < sum(store[0]["k4"]):
+    store_tile = 2 if sum(store[2]["k5"]) < 0.99 * sum(store[1]["k5"]) else 1
+print("  store kernels: K = 16 whole tile %s us, row-streamed %s us; K = 32 one tile per CTA %s us, row-streamed %s us" % (
+    ["%.1f" % x for x in store[0]["k4"]], ["%.1f" % x for x in store[1]["k4"]], ["%.1f" % x for x in store[1]["k5"]], ["%.1f" % x for x in store[2]["k5"]]))
 
 # ---------------------------------------------------------------------------------------------------
 table = {
