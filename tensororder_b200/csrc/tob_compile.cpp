@@ -65,6 +65,7 @@ Tuning& tuning() {
         x.streamk_max_tiles_log2 = TOB_TUNE_STREAMK_MAX_TILES_LOG2;
         x.streamk_max_steps = TOB_TUNE_STREAMK_MAX_STEPS;
         x.store_tile = TOB_TUNE_STORE_TILE;
+        x.ws_min_k = TOB_TUNE_WS_MIN_K;
         x.permute_low_bits = 0;
         x.permute_ctas_per_sm = 0;
         x.streamk_fix_us = TOB_TUNE_STREAMK_FIX_US;
@@ -89,7 +90,7 @@ const TuneField kTuneFields[] = {
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
     {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
-    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"streamk_max_steps", &Tuning::streamk_max_steps, nullptr}, {"store_tile", &Tuning::store_tile, nullptr},
+    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"streamk_max_steps", &Tuning::streamk_max_steps, nullptr}, {"store_tile", &Tuning::store_tile, nullptr}, {"ws_min_k", &Tuning::ws_min_k, nullptr},
     {"permute_low_bits", &Tuning::permute_low_bits, nullptr}, {"permute_ctas_per_sm", &Tuning::permute_ctas_per_sm, nullptr},
     {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };

@@ -1579,7 +1579,7 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
                 // warp-specialised pipeline, TWO producer warps issuing LDGSTS into a swizzled 4-stage ring, mbarrier
                 // full/empty stages: 34.7-35.2 TFLOP/s on the dominant joins
                 GEMM_76_WZ2<<<(unsigned)blocks, 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(p);
-            else if (kk >= 6)  // K = 64, 128: the shorter 3-stage ring fills faster
+            else if (kk >= T.ws_min_k)  // K = 32, 64, 128: the shorter 3-stage ring fills faster (K = 32 with >= 2048 tiles went to k_gemm_dmma_p1 above)
                 GEMM_76_WL<<<(unsigned)blocks, 288, gemm_ws_smem_bytes<7, 6, 3>(), stream>>>(p);
             else
                 GEMM_76<<<(unsigned)blocks, 256, gemm_smem_bytes<7, 6, 16, 3>(), stream>>>(p);

@@ -47,7 +47,7 @@ def tget(key):
 KEYS = ["gemm_min_free", "gemm_min_k", "gemm_smallk_min_free", "t1_max_k", "t1_small_out", "t1_small_max_k",
         "t32_max_k", "t32_min_out", "persist_max_k", "sm_gflops", "alone_frac", "gemm_fix_us", "reduce_gbs",
         "reduce_fix_us", "max_ksplit_log2", "min_k_per_split_log2", "force_ksplit_log2", "streamk", "streamk_min_tiles_log2",
-        "streamk_max_tiles_log2", "streamk_max_steps", "streamk_fix_us", "store_tile"] + ["gemm_min_out.%d" % i for i in range(17)]
+        "streamk_max_tiles_log2", "streamk_max_steps", "streamk_fix_us", "store_tile", "ws_min_k"] + ["gemm_min_out.%d" % i for i in range(17)]
 for k_ in KEYS:
     DEFAULTS[k_] = tget(k_)
 
@@ -279,6 +279,14 @@ for v in (0, 1, 2):  # 0: whole tile then stores; 1: rows streamed at K = 16; 2:
                 "k5": [time_join(m, n, 5)[0] for (m, n) in ((15, 14), (14, 12), (13, 11))]}
     restore()
 out["store_tile"] = store
+# K = 32 below 2048 tiles: warp-specialised ring (ws_min_k = 5) or one CTA barrier per K step (6)
+wsk = {}
+for v in (5, 6):
+    tset("ws_min_k", v)
+    wsk[v] = [time_join(m, n, 5)[0] for (m, n) in ((13, 10), (12, 10), (12, 11))]
+    restore()
+out["ws_min_k"] = wsk
+ws_min_k = 5 if sum(wsk[5]) < sum(wsk[6]) else 6
 store_tile = 0
 if sum(store[1]["k4"]) < sum(store[0]["k4"]):
     store_tile = 2 if sum(store[2]["k5"]) < 0.99 * sum(store[1]["k5"]) else 1
@@ -297,7 +305,7 @@ table = {
     "MAX_KSPLIT_LOG2": int(DEFAULTS["max_ksplit_log2"]), "MIN_K_PER_SPLIT_LOG2": int(DEFAULTS["min_k_per_split_log2"]),
     "STREAMK": 1 if wins else 0, "STREAMK_MIN_TILES_LOG2": sk_min if wins else int(DEFAULTS["streamk_min_tiles_log2"]),
     "STREAMK_MAX_TILES_LOG2": sk_max if wins else int(DEFAULTS["streamk_max_tiles_log2"]), "STREAMK_FIX_US": sk_fix, "STREAMK_MAX_STEPS": sk_steps,
-    "STORE_TILE": store_tile,
+    "STORE_TILE": store_tile, "WS_MIN_K": ws_min_k,
 }
 out["table"] = table
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)

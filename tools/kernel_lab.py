@@ -21,7 +21,7 @@ def tset(**kv):
 
 
 DEFAULTS = {}
-for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "streamk_max_steps", "store_group_log2", "store_tile", "force_ksplit_log2", "persist_max_k"):
+for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "streamk_max_steps", "store_group_log2", "store_tile", "ws_min_k", "force_ksplit_log2", "persist_max_k"):
     v = ctypes.c_double()
     assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0
     DEFAULTS[key] = v.value
@@ -90,6 +90,19 @@ def report(m, n, k, label, single, b2b):
 rows = []
 print("| m | n | k | variant | bound | single-launch us | frac | back-to-back us | frac |")
 print("|---|---|---|---|---|---|---|---|---|")
+if what == "midk":
+    for (m, n, k) in [(15, 14, 5), (14, 12, 5), (13, 11, 5), (13, 10, 5), (12, 10, 5), (15, 14, 6), (13, 10, 6), (11, 11, 7)]:
+        s0, b0, ref = time_join(m, n, k, {}, 5)
+        rows.append(report(m, n, k, "table default", s0, b0))
+        if k == 5:
+            for lab, kn in (("warp-specialised 3-stage ring (k_gemm_dmma_ws)", {"ws_min_k": 5, "store_tile": 1}), ("one tile per CTA (k_gemm_dmma)", {"store_tile": 1})):
+                s1, b1, out = time_join(m, n, k, kn, 5)
+                assert torch.equal(out, ref)
+                rows.append(report(m, n, k, lab, s1, b1))
+        elif k <= 7:
+            s1, b1, out = time_join(m, n, k, {"persist_max_k": 7, "store_tile": 0}, 5)
+            assert torch.equal(out, ref)
+            rows.append(report(m, n, k, "persistent whole-tile kernel (k_gemm_dmma_p)", s1, b1))
 if what == "streamk_long":
     for (m, n, k) in [(11, 10, 11), (11, 10, 12), (11, 10, 13), (11, 10, 14), (11, 9, 13), (10, 10, 13), (10, 9, 13), (11, 8, 12), (11, 8, 10)]:
         reps = 5
