@@ -140,7 +140,7 @@ struct Tuning {
     int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
     int permute_low_bits, permute_ctas_per_sm;  // stand-alone permutation kernel: tile shape / grid (0 = defaults)
     int ws_min_k;           // log2 K per split from which the warp-specialised kernels run (below: k_gemm_dmma, one CTA barrier per K step)
-    int store_tile;         // row-streamed persistent kernel (k_gemm_dmma_p1): 0 = never, 1 = K = 16, 2 = also K = 32 from 2048 tiles on
+    int store_tile;         // row-streamed persistent kernels: 0 = never, 1 = K = 16 (k_gemm_dmma_p1), 2 = also K = 32 from 2048 tiles on (k_gemm_dmma_wp)
 };
 Tuning& tuning();
 bool tuning_set(const char* key, double value);

@@ -628,15 +628,14 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p(KParams p) {
 // instead of overlapping; here both are fed all the time.  The B fragments of the whole K step stay in registers
 // (NB x 4 doubles), the accumulators shrink from 64 to 16 * RP registers.
 // ------------------------------------------------------------------------------------------------
-template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int RP, int KS = 1>
+template <int TM_LOG2, int TN_LOG2, int WM, int WN, int STAGES, int MINB, int RP>
 __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) {
     constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
     constexpr int NT = WM * WN * 32;
     constexpr int WTM = TM / WM, WTN = TN / WN;
     constexpr int MB = WTM / 8, NB = WTN / 8;
-    // KS = 2: K = 32, both K steps of a tile resident in one stage; the B fragments are then re-read per row group and K step
-    constexpr int TK = 16 * KS, LDS = TK + 4, CHUNKS = TK / 2, RPP = NT / CHUNKS, K4 = 4;
-    static_assert(TM % RPP == 0 && TN % RPP == 0 && MB % RP == 0 && (KS == 1 || KS == 2), "loader passes / row groups");
+    constexpr int TK = 16, LDS = TK + 4, CHUNKS = TK / 2, RPP = NT / CHUNKS, K4 = TK / 4;
+    static_assert(TM % RPP == 0 && TN % RPP == 0 && MB % RP == 0, "loader passes / row groups");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + STAGES * TM * LDS;
@@ -656,8 +655,8 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) 
     const unsigned long long total = tiles << ks;
     const int group_log2 = (p.m - TM_LOG2) < p.raster_group_log2 ? (p.m - TM_LOG2) : p.raster_group_log2;
     const int pg_log2 = group_log2 + (p.n - TN_LOG2);
-    const unsigned long long Ksplit = (1ull << k) >> ks;   // <= TK (== TK when KS == 2)
-    const int k4_end = KS == 1 ? (int)((Ksplit + 3) / 4) : K4;
+    const unsigned long long Ksplit = (1ull << k) >> ks;   // <= TK
+    const int k4_end = (int)((Ksplit + 3) / 4);
     const long long nmine = total > blockIdx.x ? (long long)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
     const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
@@ -722,40 +721,28 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) k_gemm_dmma_p1(KParams p) 
         double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
         const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
         double bf[NB][K4];
-        if (KS == 1) {
 #pragma unroll
-            for (int j = 0; j < NB; j++)
+        for (int j = 0; j < NB; j++)
 #pragma unroll
-                for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = (k4 < k4_end) ? bs[j * 8 * LDS + k4 * 4] : 0.0;
-        }
+            for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = (k4 < k4_end) ? bs[j * 8 * LDS + k4 * 4] : 0.0;
 #pragma unroll
         for (int i0 = 0; i0 < MB; i0 += RP) {
             double acc[RP][NB][2];
+            double af[RP][K4];
 #pragma unroll
-            for (int r = 0; r < RP; r++)
+            for (int r = 0; r < RP; r++) {
+#pragma unroll
+                for (int k4 = 0; k4 < K4; k4++) af[r][k4] = (k4 < k4_end) ? as[(i0 + r) * 8 * LDS + k4 * 4] : 0.0;
 #pragma unroll
                 for (int j = 0; j < NB; j++) acc[r][j][0] = acc[r][j][1] = 0.0;
+            }
 #pragma unroll
-            for (int h = 0; h < KS; h++) {
-                double af[RP][K4];
+            for (int k4 = 0; k4 < K4; k4++) {
+                if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
 #pragma unroll
                 for (int r = 0; r < RP; r++)
 #pragma unroll
-                    for (int k4 = 0; k4 < K4; k4++) af[r][k4] = (k4 < k4_end) ? as[(i0 + r) * 8 * LDS + h * 16 + k4 * 4] : 0.0;
-                if (KS > 1) {
-#pragma unroll
-                    for (int j = 0; j < NB; j++)
-#pragma unroll
-                        for (int k4 = 0; k4 < K4; k4++) bf[j][k4] = bs[j * 8 * LDS + h * 16 + k4 * 4];
-                }
-#pragma unroll
-                for (int k4 = 0; k4 < K4; k4++) {
-                    if (k4 >= k4_end) break;  // K = 2, 4, 8: the zero-filled tail of the K step adds nothing
-#pragma unroll
-                    for (int r = 0; r < RP; r++)
-#pragma unroll
-                        for (int j = 0; j < NB; j++) dmma884(acc[r][j][0], acc[r][j][1], af[r][k4], bf[j][k4]);
-                }
+                    for (int j = 0; j < NB; j++) dmma884(acc[r][j][0], acc[r][j][1], af[r][k4], bf[j][k4]);
             }
             unsigned long long rb[RP];
 #pragma unroll
@@ -969,6 +956,173 @@ __global__ void __launch_bounds__(WM * WN * 32 + 32 * NPROD, MINB) k_gemm_dmma_w
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent + warp-specialised + row-streamed: the short-K joins (K = 16 per tile, or K = 32 as two ring stages) without a
+// CTA barrier in the steady state.  k_gemm_dmma_p1 brings every warp of the CTA to a __syncthreads per tile (ncu: barrier
+// stall 1.2 per issued instruction, DMMA pipe 77 % busy at K = 32); here producer warps walk the CTA's tiles
+// (blockIdx.x + j * gridDim.x) and fill a 4-stage ring of swizzled K steps, each consumer warp waits for the stages of its
+// tile on the `full` mbarriers, computes its 32x32 block RP row groups at a time, stores each group while the next
+// computes, and hands the stages back on `empty`.  Same tiling, swizzle and fragment layout as k_gemm_dmma_ws.
+// ------------------------------------------------------------------------------------------------
+template <int STAGES, int NPROD, int RP, int KS>
+__global__ void __launch_bounds__(256 + 32 * NPROD, 2) k_gemm_dmma_wp(KParams p) {
+    constexpr int TM_LOG2 = 7, TN_LOG2 = 6, WM = 4, WN = 2;
+    constexpr int TM = 1 << TM_LOG2, TN = 1 << TN_LOG2;
+    constexpr int NC = WM * WN * 32;
+    constexpr int TK = 16, LDS = TK, K4 = TK / 4;
+    constexpr int WTM = TM / WM, WTN = TN / WN;
+    constexpr int MB = WTM / 8, NB = WTN / 8;
+    static_assert(MB % RP == 0 && STAGES % KS == 0, "row groups / stages per tile");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * TM * LDS;
+    unsigned long long* cM = reinterpret_cast<unsigned long long*>(Bs + STAGES * TN * LDS);
+    unsigned long long* cN = cM + TM;
+    unsigned long long* full = cN + TN;
+    unsigned long long* empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = p.k, ks = p.ksplit_log2;
+    const int tiles_log2 = (p.m - TM_LOG2) + (p.n - TN_LOG2);
+    const unsigned long long tiles = 1ull << tiles_log2;
+    const unsigned long long total = tiles << ks;
+    const int group_log2 = (p.m - TM_LOG2) < p.raster_group_log2 ? (p.m - TM_LOG2) : p.raster_group_log2;
+    const int pg_log2 = group_log2 + (p.n - TN_LOG2);
+    const unsigned long long Ksplit = (1ull << k) >> ks;   // == TK * KS
+    const long long nmine = total > blockIdx.x ? (long long)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    auto decode = [&](unsigned long long id, unsigned long long& split, unsigned long long& tile_m, unsigned long long& tile_n) {
+        split = id >> tiles_log2;
+        const unsigned long long tid_in = id & (tiles - 1);
+        const unsigned long long gidx = tid_in >> pg_log2, r = tid_in & ((1ull << pg_log2) - 1ull);
+        tile_m = (gidx << group_log2) + (r & ((1ull << group_log2) - 1ull));
+        tile_n = r >> group_log2;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 32 * NPROD);
+            mbar_init(&empty[s], WM * WN);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < TM; i += NC + 32 * NPROD) cM[i] = pdep_runs((unsigned long long)i, p.runs_m);
+    for (int i = tid; i < TN; i += NC + 32 * NPROD) cN[i] = pdep_runs((unsigned long long)i, p.runs_n);
+    __syncthreads();
+
+    if (warp >= WM * WN) {
+        // ===================== producer warps: one ring stage per K step, tile after tile =====================
+        const int pw = warp - WM * WN;
+        const double* Abase = operand_base(p.a, p.leaf_off, p.a_leaf);
+        const double* Bbase = operand_base(p.b, p.leaf_off, p.b_leaf);
+        const int chunk = lane & 7, r0 = lane >> 3;
+        const int dchunk = chunk ^ (r0 << 1);
+        const unsigned long long step = (4ull * NPROD) << k;
+        const unsigned long long lane_off = ((unsigned long long)(r0 + 4 * pw) << k) + chunk * 2;
+        const int dst_off = (r0 + 4 * pw) * LDS + dchunk * 2;
+        long long it = 0;
+        for (long long j = 0; j < nmine; j++) {
+            unsigned long long split, tile_m, tile_n;
+            decode(blockIdx.x + (unsigned long long)j * gridDim.x, split, tile_m, tile_n);
+            const double* a_lane = Abase + ((tile_m << TM_LOG2) << k) + split * Ksplit + lane_off;
+            const double* b_lane = Bbase + ((tile_n << TN_LOG2) << k) + split * Ksplit + lane_off;
+#pragma unroll
+            for (int h = 0; h < KS; h++, it++) {
+                const int s = (int)(it % STAGES);
+                if (it >= STAGES) mbar_wait(&empty[s], (unsigned)(((it / STAGES) - 1) & 1));
+                const double* ag = a_lane + h * TK;
+                const double* bg = b_lane + h * TK;
+                double* ad = As + s * TM * LDS + dst_off;
+                double* bd = Bs + s * TN * LDS + dst_off;
+#pragma unroll
+                for (int i = 0; i < TM / 4 / NPROD; i++) cp_async16(ad + i * (4 * NPROD * LDS), ag + i * step);
+#pragma unroll
+                for (int i = 0; i < TN / 4 / NPROD; i++) cp_async16(bd + i * (4 * NPROD * LDS), bg + i * step);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(&full[s]))
+                             : "memory");
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % WM, wn = warp / WM;
+    const int frag_off_a = (wm * WTM + g) * LDS;
+    const int frag_off_b = (wn * WTN + g) * LDS;
+    int koff[K4];
+#pragma unroll
+    for (int k4 = 0; k4 < K4; k4++) koff[k4] = (((2 * k4 + (t >> 1)) ^ ((g & 3) << 1)) << 1) + (t & 1);
+    const bool vec = (p.mask_n & 1ull) != 0;
+    long long it = 0;
+    for (long long j = 0; j < nmine; j++, it += KS) {
+        unsigned long long split, tile_m, tile_n;
+        decode(blockIdx.x + (unsigned long long)j * gridDim.x, split, tile_m, tile_n);
+        double* Cout = (ks > 0) ? p.ws + (split << (p.m + p.n)) : p.c;
+        const unsigned long long cbase = pdep_runs(tile_m << TM_LOG2, p.runs_m) | pdep_runs(tile_n << TN_LOG2, p.runs_n);
+#pragma unroll
+        for (int h = 0; h < KS; h++) mbar_wait(&full[(int)((it + h) % STAGES)], (unsigned)(((it + h) / STAGES) & 1));
+        const int s0 = (int)(it % STAGES);  // KS divides STAGES: the tile's stages are s0 .. s0 + KS - 1
+        double bf[NB][K4];
+        if (KS == 1) {
+#pragma unroll
+            for (int jj = 0; jj < NB; jj++)
+#pragma unroll
+                for (int k4 = 0; k4 < K4; k4++) bf[jj][k4] = Bs[s0 * TN * LDS + frag_off_b + jj * 8 * LDS + koff[k4]];
+        }
+#pragma unroll
+        for (int i0 = 0; i0 < MB; i0 += RP) {
+            double acc[RP][NB][2];
+#pragma unroll
+            for (int r = 0; r < RP; r++)
+#pragma unroll
+                for (int jj = 0; jj < NB; jj++) acc[r][jj][0] = acc[r][jj][1] = 0.0;
+#pragma unroll
+            for (int h = 0; h < KS; h++) {
+                const double* as = As + (s0 + h) * TM * LDS + frag_off_a;
+                double af[RP][K4];
+#pragma unroll
+                for (int r = 0; r < RP; r++)
+#pragma unroll
+                    for (int k4 = 0; k4 < K4; k4++) af[r][k4] = as[(i0 + r) * 8 * LDS + koff[k4]];
+                if (KS > 1) {
+#pragma unroll
+                    for (int jj = 0; jj < NB; jj++)
+#pragma unroll
+                        for (int k4 = 0; k4 < K4; k4++) bf[jj][k4] = Bs[(s0 + h) * TN * LDS + frag_off_b + jj * 8 * LDS + koff[k4]];
+                }
+#pragma unroll
+                for (int k4 = 0; k4 < K4; k4++)
+#pragma unroll
+                    for (int r = 0; r < RP; r++)
+#pragma unroll
+                        for (int jj = 0; jj < NB; jj++) dmma884(acc[r][jj][0], acc[r][jj][1], af[r][k4], bf[jj][k4]);
+            }
+            if (i0 + RP >= MB) {
+                // the last row group's fragments are in registers (its DMMAs were issued behind the loads): the stages can be refilled
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int h = 0; h < KS; h++) mbar_arrive(&empty[s0 + h]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RP; r++) {
+                const unsigned long long rbase = cbase | cM[wm * WTM + (i0 + r) * 8 + g];
+#pragma unroll
+                for (int jj = 0; jj < NB; jj++) {
+                    const int col = wn * WTN + jj * 8 + 2 * t;
+                    if (vec) {
+                        *reinterpret_cast<double2*>(Cout + (rbase | cN[col])) = make_double2(acc[r][jj][0], acc[r][jj][1]);
+                    } else {
+                        Cout[rbase | cN[col]] = acc[r][jj][0];
+                        Cout[rbase | cN[col + 1]] = acc[r][jj][1];
+                    }
+                }
+            }
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Stream-K form of the warp-specialised kernel, for joins whose tile count quantises badly on the CTA slots
@@ -1241,7 +1395,10 @@ constexpr size_t gemm_smem_bytes() {
 // three CTAs per SM at 80 registers (0.80), stores deferred behind the next group's DMMAs (0.83), 64x64 tiles at four
 // CTAs per SM on k_gemm_dmma_p (0.83, and 0.73 instead of 0.72 of the FP64 peak at k = 5).
 #define GEMM_76_P1 k_gemm_dmma_p1<7, 6, 4, 2, 3, 2, 2>
-#define GEMM_76_P2 k_gemm_dmma_p1<7, 6, 4, 2, 2, 2, 2, 2>   // K = 32: two K steps per stage, two stages (three do not fit twice per SM)
+// K = 32 as two ring stages per tile, two producer warps.  Measured next to it (profiles/r02i_kernel_lab_k32.md): one producer
+// warp (0.81 instead of 0.85 at m=15,n=14,k=5), k_gemm_dmma_p1 with both K steps in one stage and a CTA barrier per tile (0.79),
+// and the same kernel for K = 16 (0.80-0.82 where k_gemm_dmma_p1 reaches 0.89: kept there).
+#define GEMM_76_WP2 k_gemm_dmma_wp<4, 2, 2, 2>
 #define GEMM_76_WL k_gemm_dmma_ws<7, 6, 4, 2, 3, 2, false, false>
 #define GEMM_76_WZ2 k_gemm_dmma_ws<7, 6, 4, 2, 4, 2, false, true, 2>
 #define GEMM_76_SK k_gemm_dmma_sk<7, 6, 4, 2, 4, 2, 2>
@@ -1264,7 +1421,7 @@ cudaError_t configure_kernels() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_P1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 16, 3>());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(GEMM_76_P2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<7, 6, 32, 2>());
+    e = cudaFuncSetAttribute(GEMM_76_WP2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 4, true>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(GEMM_76_WL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_ws_smem_bytes<7, 6, 3>());
     if (e != cudaSuccess) return e;
@@ -1553,11 +1710,11 @@ cudaError_t launch_contract(const Op& op, const KParams& p, cudaStream_t stream,
             const Tuning& T = tuning();
             const int kk = op.k - op.ksplit_log2;  // log2 of the K range one CTA walks
             if (kk == 5 && T.store_tile == 2 && blocks >= 2048) {
-                // K = 32, >= 2048 tiles (tensor time 1.5x the store time): the row-streamed persistent kernel with both K steps
-                // resident: 0.72 -> 0.79 of the FP64 peak at m=15,n=14; at 1024 tiles the one-tile-per-CTA kernel is 4 % faster
+                // K = 32, >= 2048 tiles (tensor time 1.5x the store time): persistent, warp-specialised, rows stored while the
+                // next rows compute: 0.72 -> 0.85 of the FP64 peak at m=15,n=14; at 1024 tiles the 3-stage ring below is as fast
                 KParams pp = p;
                 pp.raster_group_log2 = T.store_group_log2;
-                GEMM_76_P2<<<2 * num_sms(), 256, gemm_smem_bytes<7, 6, 32, 2>(), stream>>>(pp);
+                GEMM_76_WP2<<<2 * num_sms(), 320, gemm_ws_smem_bytes<7, 6, 4, true>(), stream>>>(pp);
             } else if (kk <= T.persist_max_k && blocks > 2ull * (unsigned long long)num_sms())
                 // short K, more tiles than CTA slots (the store-bound joins): persistent CTAs prefetch the next tiles
                 // (a shared-memory-staged epilogue writing 512-byte runs was measured in round 2 and is 25-30 % SLOWER than

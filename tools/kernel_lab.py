@@ -125,11 +125,12 @@ if what in ("streamk", "all"):
         s2, b2, out = time_join(m, n, k, {}, reps)
         rows.append(report(m, n, k, "table default", s2, b2))
 if what in ("store", "all"):
-    for (m, n, k) in [(14, 14, 4), (15, 15, 4), (14, 14, 2), (16, 16, 2), (15, 14, 3), (14, 13, 1), (13, 11, 4), (15, 14, 5), (14, 12, 5), (13, 11, 5), (13, 10, 5)]:
+    for (m, n, k) in [(14, 14, 4), (15, 15, 4), (13, 11, 4), (12, 10, 4), (15, 14, 5), (14, 12, 5), (13, 11, 5), (13, 10, 5)]:
         ref = None
         variants = [("whole tile, then stores (k_gemm_dmma_p)", {"store_tile": 0}), ("table default", {})]
         if k == 5:
-            variants = [("one tile per CTA (k_gemm_dmma)", {"store_tile": 1}), ("row-streamed persistent, K = 32 resident", {"store_tile": 2})]
+            variants = [("one tile per CTA (k_gemm_dmma)", {"store_tile": 1, "ws_min_k": 6}), ("warp-specialised 3-stage ring (k_gemm_dmma_ws)", {"store_tile": 1}),
+                        ("table default", {})]
         for label, knobs in variants:
             s, b, out = time_join(m, n, k, knobs, 3)
             if ref is None:
