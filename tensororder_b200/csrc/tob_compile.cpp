@@ -66,6 +66,7 @@ Tuning& tuning() {
         x.streamk_max_steps = TOB_TUNE_STREAMK_MAX_STEPS;
         x.store_tile = TOB_TUNE_STORE_TILE;
         x.ws_min_k = TOB_TUNE_WS_MIN_K;
+        x.t256_ctas_log2 = TOB_TUNE_T256_CTAS_LOG2;
         x.permute_low_bits = 0;
         x.permute_ctas_per_sm = 0;
         x.streamk_fix_us = TOB_TUNE_STREAMK_FIX_US;
@@ -90,7 +91,7 @@ const TuneField kTuneFields[] = {
     {"max_ksplit_log2", &Tuning::max_ksplit_log2, nullptr}, {"min_k_per_split_log2", &Tuning::min_k_per_split_log2, nullptr},
     {"force_ksplit_log2", &Tuning::force_ksplit_log2, nullptr},
     {"streamk", &Tuning::streamk, nullptr}, {"streamk_min_tiles_log2", &Tuning::streamk_min_tiles_log2, nullptr},
-    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"streamk_max_steps", &Tuning::streamk_max_steps, nullptr}, {"store_tile", &Tuning::store_tile, nullptr}, {"ws_min_k", &Tuning::ws_min_k, nullptr},
+    {"streamk_max_tiles_log2", &Tuning::streamk_max_tiles_log2, nullptr}, {"streamk_max_steps", &Tuning::streamk_max_steps, nullptr}, {"store_tile", &Tuning::store_tile, nullptr}, {"ws_min_k", &Tuning::ws_min_k, nullptr}, {"t256_ctas_log2", &Tuning::t256_ctas_log2, nullptr},
     {"permute_low_bits", &Tuning::permute_low_bits, nullptr}, {"permute_ctas_per_sm", &Tuning::permute_ctas_per_sm, nullptr},
     {"streamk_fix_us", nullptr, &Tuning::streamk_fix_us}, {"store_group_log2", &Tuning::store_group_log2, nullptr},
 };
@@ -224,7 +225,7 @@ void choose_kernel(Op* op, int32_t kernel_policy, bool allow_splitk) {
     if (op->threads_per_out == 256 && allow_splitk) {
         // one CTA per (output, k-chunk); want >= 4 CTAs per SM, chunks of >= 2^12 elements
         int ks = 0;
-        while (outs + ks < 10 && (k - ks) > 12) ks++;
+        while (outs + ks < T.t256_ctas_log2 && (k - ks) > 12) ks++;
         op->ksplit_log2 = ks;
     }
 }

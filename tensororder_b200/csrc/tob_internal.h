@@ -139,6 +139,7 @@ struct Tuning {
     double streamk_fix_us;  // modelled cost of the partial-tile exchange
     int store_group_log2;   // persistent short-K kernel: M-tiles per raster group (0: N-tiles fastest)
     int permute_low_bits, permute_ctas_per_sm;  // stand-alone permutation kernel: tile shape / grid (0 = defaults)
+    int t256_ctas_log2;     // CTA-per-output kernel: K is split until outputs * splits reach 2^this CTAs (chunks stay >= 2^12 elements)
     int ws_min_k;           // log2 K per split from which the warp-specialised kernels run (below: k_gemm_dmma, one CTA barrier per K step)
     int store_tile;         // row-streamed persistent kernels: 0 = never, 1 = K = 16 (k_gemm_dmma_p1), 2 = also K = 32 from 2048 tiles on (k_gemm_dmma_wp)
 };

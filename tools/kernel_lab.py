@@ -21,7 +21,7 @@ def tset(**kv):
 
 
 DEFAULTS = {}
-for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "streamk_max_steps", "store_group_log2", "store_tile", "ws_min_k", "force_ksplit_log2", "persist_max_k"):
+for key in ("streamk", "streamk_min_tiles_log2", "streamk_max_tiles_log2", "streamk_max_steps", "store_group_log2", "store_tile", "ws_min_k", "t256_ctas_log2", "force_ksplit_log2", "persist_max_k"):
     v = ctypes.c_double()
     assert cabi.lib.tob_tuning_get(key.encode(), ctypes.byref(v)) == 0
     DEFAULTS[key] = v.value
@@ -90,6 +90,11 @@ def report(m, n, k, label, single, b2b):
 rows = []
 print("| m | n | k | variant | bound | single-launch us | frac | back-to-back us | frac |")
 print("|---|---|---|---|---|---|---|---|---|")
+if what == "dot":
+    for (m, n, k) in [(0, 0, 24), (0, 0, 26), (0, 0, 22), (1, 1, 23), (2, 1, 22), (3, 3, 20)]:
+        for v in (10, 11, 12, 13):
+            s0, b0, out = time_join(m, n, k, {"t256_ctas_log2": v}, 10)
+            rows.append(report(m, n, k, "CTA per (output, chunk), 2^%d CTAs" % v, s0, b0))
 if what == "midk":
     for (m, n, k) in [(15, 14, 5), (14, 12, 5), (13, 11, 5), (13, 10, 5), (12, 10, 5), (15, 14, 6), (13, 10, 6), (11, 11, 7)]:
         s0, b0, ref = time_join(m, n, k, {}, 5)
