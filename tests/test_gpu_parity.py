@@ -37,12 +37,16 @@ def test_readme_instance():
     assert str(got) == "2802717837.0"  # what `Count:` prints, tensororder.py:299
 
 
-@pytest.mark.parametrize("name", [n for n in ALL if "count" in load_golden(n).expected])
-@pytest.mark.parametrize("policy", [0, 1])
+def _unsliced_cases():
+    """(name, kernel policy): every fixture with a stored count on the dispatch table; the generic-kernels-only policy
+    (a debug path, far too slow for the big GEMM nodes) up to max-rank 24."""
+    names = [n for n in ALL if "count" in load_golden(n).expected]
+    return [(n, 0) for n in names] + [(n, 1) for n in names if load_golden(n).expected["maxrank"] <= 24]
+
+
+@pytest.mark.parametrize("name,policy", _unsliced_cases())
 def test_unsliced_counts(name, policy):
     pp = load_golden(name)
-    if policy == 1 and pp.expected["maxrank"] > 24:
-        pytest.skip("generic-only policy is a debug path; too slow for the big GEMM nodes")
     api = _api(kernel_policy=policy)
     got = api.contract_sliced(pp.as_execution_plan())
     _check(got, pp.expected)
