@@ -286,13 +286,15 @@ class PlanCache:
     groups' contents and the compile options.  `execution.run`'s OOM retry (src/execution.py:140-142)
     changes `groups_to_slice` and `contract_small` (sliced_execution_plan.py:29-56) replaces `plan.tree`,
     so both miss.  A hit skips the tree walk and the plan compile; the LEAF VALUES are re-read through
-    `Tensor.build()` and copied host -> device on every call.  Small plans (arena <= 256 MiB, 1 GiB in
-    total) stay resident on the device with their captured CUDA graphs; larger ones give their arena back
-    after each call and keep only the compiled program."""
+    `Tensor.build()` and copied host -> device on every call.  Plans up to 2 GiB (8 GiB in total, least
+    recently used first out) stay resident on the device with their captured CUDA graphs; larger ones give
+    their arena back after each call and keep only the compiled program."""
 
     MAX_ENTRIES = 64
-    RESIDENT_PLAN_BYTES = 256 << 20
-    RESIDENT_TOTAL_BYTES = 1 << 30
+    # the same footprint the library's block pool keeps cached anyway (blocks up to 4 GiB, 8 GiB per device): a released
+    # arena only moves from the plan to the pool, and the next call pays a full upload (tables, prefix copy) to get it back
+    RESIDENT_PLAN_BYTES = 2 << 30
+    RESIDENT_TOTAL_BYTES = 8 << 30
 
     def __init__(self):
         self.entries = OrderedDict()
