@@ -177,3 +177,35 @@ def test_plan_cache_with_two_host_threads(fake):
         assert all(v == 2802717837.0 for v in fa.result() + fa2.result())
         assert all(v == pytest.approx(want_b, rel=1e-12) for v in fb.result())
     assert all(e["compiled"].busy == 0 for e in PLAN_CACHE.entries.values())
+
+
+def test_collective_order_serves_tickets_in_order_and_rejects_stale_ones():
+    """api.CollectiveOrder: threads pass the turnstile in ticket order whatever their arrival order; a ticket that was
+    already served is an error rather than a silent re-ordering."""
+    import threading
+    import time
+
+    from tensororder_b200.api import CollectiveOrder
+
+    order, served = CollectiveOrder(), []
+
+    def worker(ticket, delay):
+        time.sleep(delay)
+        order.enter(ticket)
+        served.append(ticket)
+        order.leave(ticket)
+
+    threads = [threading.Thread(target=worker, args=(t, 0.02 * (4 - t))) for t in range(5)]  # arrive 4, 3, 2, 1, 0
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(10)
+        assert not t.is_alive()
+    assert served == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        order.enter(2)
+    order.enter(5)
+    order.leave(5)
+    api = B200API()
+    with pytest.raises(ValueError):
+        api.add_argument("collective_ticket", (object(), 0))
