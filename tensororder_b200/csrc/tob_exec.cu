@@ -1314,20 +1314,28 @@ int tob_tensordot_host(const double* a, int32_t rank_a, const double* b, int32_t
         set_error("bad tensordot arguments");
         return TOB_E_INVALID;
     }
-    int rc = ensure_device(0);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int rc = ensure_device(dev);
     if (rc != TOB_OK) return rc;
     const int rank_c = rank_a + rank_b - 2 * n_axes;
     const size_t na = (size_t)8 << rank_a, nb = (size_t)8 << rank_b, nc = (size_t)8 << rank_c;
     const size_t nws = na + nb + (nc << 4) + 256;
-    double *da = nullptr, *db = nullptr, *dc = nullptr, *dws = nullptr;
-    auto cleanup = [&]() { cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dws); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&da, na)) != cudaSuccess || (e = cudaMalloc(&db, nb)) != cudaSuccess ||
-        (e = cudaMalloc(&dc, nc)) != cudaSuccess || (e = cudaMalloc(&dws, nws)) != cudaSuccess) {
-        cleanup();
+    // ONE block from the pool (operands, result, workspace): cudaMalloc / cudaFree per call cost milliseconds, and cudaFree
+    // waits for everything else in flight on the device (other host threads' contractions)
+    const size_t oa = 0, ob = align_up(oa + na, 256), oc = align_up(ob + nb, 256), ows = align_up(oc + nc, 256);
+    Block blk;
+    cudaError_t e = pool_acquire(ows + nws, dev, false, &blk);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
         set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? TOB_E_OOM : TOB_E_CUDA;
     }
+    char* base = static_cast<char*>(blk.ptr);
+    double* da = reinterpret_cast<double*>(base + oa);
+    double* db = reinterpret_cast<double*>(base + ob);
+    double* dc = reinterpret_cast<double*>(base + oc);
+    double* dws = reinterpret_cast<double*>(base + ows);
     rc = TOB_OK;
     if ((e = cudaMemcpy(da, a, na, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(db, b, nb, cudaMemcpyHostToDevice)) != cudaSuccess) {
@@ -1339,7 +1347,7 @@ int tob_tensordot_host(const double* a, int32_t rank_a, const double* b, int32_t
         set_error(std::string("cudaMemcpy: ") + cudaGetErrorString(e));
         rc = TOB_E_CUDA;
     }
-    cleanup();
+    pool_release(blk);
     return rc;
 }
 
