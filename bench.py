@@ -25,11 +25,15 @@ the ranks (longest first, by the compiled programs' cost); one NCCL all-reduce c
   e2e   : the same workload through the reference-facing call `B200API.contract_sliced(plan)` with HOST
           leaf buffers: leaf build (`Tensor.build`) + pinned H2D of the leaves + kernels + D2H of the count
           inside the timed region, every step; the plan compile is paid once per plan (plan cache keyed
-          by plan identity) in the untimed warm-up pass.  Two host threads make the calls: one
-          contracts the sliced instances (their all-reduces must come in the same order on every rank), the
-          other the rank's unsliced instances, so small contractions overlap the large ones' GEMMs.
+          by plan identity) in the first of two untimed warm-up passes.  A pool of host threads
+          (8 at N = 1) makes the calls, so small contractions overlap the large ones' GEMMs; at N > 1 every sliced
+          instance has a thread and a collective ticket of its own (api.CollectiveOrder: the contractions overlap,
+          their all-reduces are issued in the same order on every rank).
   extra : BASELINE configs 3, 4 and 5 measured in the same run: `weighted150` (n=150 mcc weights,
-          factor-Flow), `sliced250` (n=250, 8 slices, at this N), `rank_sweep` (N=1).
+          factor-Flow), `sliced250` (n=250, 8 slices, at this N), `rank_sweep` (N=1; single timed launches and
+          the same launches back to back).
+  rank_split : per rank, where the device time goes (replicated prologues / own slices / owned unsliced
+          instances / the count all-reduce).
   --impl reference : the REAL reference (oracle/_ref: vardigroup/TensorOrder's own
           `NumpyAPI.contract_sliced` on reference objects rebuilt from the same stored plans) on all host
           cores, over the same 18 instances.
